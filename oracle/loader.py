@@ -1,0 +1,239 @@
+"""ctypes front-end for the two CPU checkers.  TEST / BENCH INFRASTRUCTURE ONLY.
+
+* ``port()``  -> oracle/_build/libmeshopt_oracle.so : our C restatement (oracle_* symbols)
+* ``ref()``   -> oracle/_ref/libmeshopt_ref.so      : the unmodified reference (meshopt_* symbols),
+                 present only when it was built in a container that has /root/reference
+
+Only tests/, __graft_entry__.smoke() and bench.py (input generation with the reference encoder,
+cpu_baseline leg, --impl reference arm) may import this module.  The product package
+``meshoptimizer_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_uint64, c_void_p
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "_build", "libmeshopt_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libmeshopt_ref.so")
+
+FILTER_NONE, FILTER_OCT, FILTER_QUAT, FILTER_EXP, FILTER_COLOR = 0, 1, 2, 3, 4
+FILTER_NAMES = {"none": 0, "oct": 1, "quat": 2, "exp": 3, "color": 4}
+
+
+class HarnessStream(ctypes.Structure):
+    _fields_ = [
+        ("src", c_void_p),
+        ("src_size", c_size_t),
+        ("dst", c_void_p),
+        ("vertex_count", c_size_t),
+        ("vertex_size", c_size_t),
+        ("filter", c_int),
+        ("status", c_int),
+    ]
+
+
+def build(force: bool = False) -> None:
+    """Compile the port (always) and the reference library (when /root/reference exists)."""
+    if force or not os.path.exists(PORT_SO) or _stale(PORT_SO):
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    if os.path.isdir("/root/reference/src") and (force or not os.path.exists(REF_SO) or _stale(REF_SO)):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+
+
+def _stale(so: str) -> bool:
+    t = os.path.getmtime(so)
+    srcs = ["vertexcodec_oracle.c", "vertexfilter_oracle.c", "harness.cpp", "Makefile"]
+    return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in srcs)
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray, memoryview)) else a).view(np.uint8).reshape(-1)
+
+
+class _Lib:
+    """Common wrapper: decode + filters + multi-threaded harness, for either library."""
+
+    def __init__(self, path: str, prefix: str, kind: str):
+        self.path = path
+        self.kind = kind
+        self.lib = ctypes.CDLL(path, mode=os.RTLD_LOCAL)  # RTLD_LOCAL: never collide with our own meshopt_* exports
+        L = self.lib
+        self._decode = getattr(L, prefix + "decodeVertexBuffer")
+        self._decode.restype = c_int
+        self._decode.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+        self._version = getattr(L, prefix + "decodeVertexVersion")
+        self._version.restype = c_int
+        self._version.argtypes = [c_void_p, c_size_t]
+        self._filters = {}
+        for name in ("Oct", "Quat", "Exp", "Color"):
+            f = getattr(L, prefix + "decodeFilter" + name)
+            f.restype = None
+            f.argtypes = [c_void_p, c_size_t, c_size_t]
+            self._filters[name.lower()] = f
+        L.harness_decode_mt.restype = c_double
+        L.harness_decode_mt.argtypes = [POINTER(HarnessStream), c_size_t, c_int, c_int, POINTER(c_double)]
+        L.harness_hw_threads.restype = c_int
+        L.harness_gen_grid.argtypes = [c_void_p, c_int]
+        L.harness_gen_js16.argtypes = [c_void_p, c_size_t]
+        L.harness_gen_c2.argtypes = [c_void_p, c_uint64, c_size_t, c_int]
+
+    # -- single calls ---------------------------------------------------------------------------
+    def decode_vertex_buffer(self, vertex_count: int, vertex_size: int, data) -> tuple[int, np.ndarray]:
+        src = _u8(data)
+        out = np.zeros(max(vertex_count * vertex_size, 1), dtype=np.uint8)
+        rc = self._decode(out.ctypes.data, vertex_count, vertex_size, src.ctypes.data if src.size else None, src.size)
+        return rc, out[: vertex_count * vertex_size]
+
+    def decode_vertex_version(self, data) -> int:
+        src = _u8(data)
+        return self._version(src.ctypes.data if src.size else None, src.size)
+
+    def decode_filter(self, name: str, buf: np.ndarray, count: int, stride: int) -> np.ndarray:
+        out = np.ascontiguousarray(buf).view(np.uint8).reshape(-1).copy()
+        assert out.size >= count * stride
+        self._filters[name](out.ctypes.data, count, stride)
+        return out
+
+    # -- batch, multi-threaded (cpu baseline) --------------------------------------------------------
+    def decode_batch_mt(self, streams, threads: int, passes: int = 1):
+        """streams: list of (src u8 array, vertex_count, vertex_size, filter id).
+        Returns (best_seconds, per_pass_seconds, outputs list, statuses)."""
+        n = len(streams)
+        arr = (HarnessStream * n)()
+        outs = []
+        keep = []
+        for i, (src, count, vs, filt) in enumerate(streams):
+            s = _u8(src)
+            keep.append(s)
+            o = np.zeros(max(count * vs, 1), dtype=np.uint8)
+            outs.append(o)
+            arr[i].src = s.ctypes.data
+            arr[i].src_size = s.size
+            arr[i].dst = o.ctypes.data
+            arr[i].vertex_count = count
+            arr[i].vertex_size = vs
+            arr[i].filter = filt
+        times = (c_double * passes)()
+        best = self.lib.harness_decode_mt(arr, n, threads, passes, times)
+        return best, list(times), [o[: c * v] for o, (_, c, v, _) in zip(outs, streams)], [arr[i].status for i in range(n)]
+
+    def hw_threads(self) -> int:
+        return int(self.lib.harness_hw_threads())
+
+    # -- synthetic vertex data -------------------------------------------------------------------------
+    def gen_grid(self, side: int) -> np.ndarray:
+        out = np.empty(((side + 1) * (side + 1), 16), dtype=np.uint16)
+        self.lib.harness_gen_grid(out.ctypes.data, side)
+        return out
+
+    def gen_js16(self, vertex_count: int) -> np.ndarray:
+        out = np.empty((vertex_count, 16), dtype=np.uint8)
+        self.lib.harness_gen_js16(out.ctypes.data, vertex_count)
+        return out
+
+    def gen_c2(self, first: int, count: int, threads: int = 0) -> np.ndarray:
+        out = np.empty((count, 16), dtype=np.uint16)
+        self.lib.harness_gen_c2(out.ctypes.data, first, count, threads or self.hw_threads())
+        return out
+
+
+class _Ref(_Lib):
+    """The unmodified reference: adds the encoders (input generation)."""
+
+    def __init__(self):
+        super().__init__(REF_SO, "meshopt_", "reference")
+        L = self.lib
+        L.meshopt_encodeVertexBufferLevel.restype = c_size_t
+        L.meshopt_encodeVertexBufferLevel.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_int]
+        L.meshopt_encodeVertexBufferBound.restype = c_size_t
+        L.meshopt_encodeVertexBufferBound.argtypes = [c_size_t, c_size_t]
+        L.harness_encode_segments.restype = None
+        L.harness_encode_segments.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+        L.harness_grid_reorder.argtypes = [c_void_p, c_int]
+        for name, extra in (("Oct", []), ("Quat", []), ("Color", []), ("Exp", [c_int])):
+            f = getattr(L, "meshopt_encodeFilter" + name)
+            f.restype = None
+            f.argtypes = [c_void_p, c_size_t, c_size_t, c_int, c_void_p] + extra
+
+    def encode_bound(self, vertex_count: int, vertex_size: int) -> int:
+        return int(self.lib.meshopt_encodeVertexBufferBound(vertex_count, vertex_size))
+
+    def encode_vertex_buffer(self, vertices: np.ndarray, vertex_count: int, vertex_size: int, level: int = 2, version: int = 1) -> np.ndarray:
+        v = _u8(vertices)
+        assert v.size >= vertex_count * vertex_size
+        buf = np.empty(self.encode_bound(vertex_count, vertex_size), dtype=np.uint8)
+        n = self.lib.meshopt_encodeVertexBufferLevel(buf.ctypes.data, buf.size, v.ctypes.data if v.size else None, vertex_count, vertex_size, level, version)
+        assert n > 0
+        return buf[:n].copy()
+
+    def encode_segments(self, vertices: np.ndarray, vertex_size: int, firsts, counts, level: int = 2, version: int = 1, threads: int = 0):
+        """Encode independent segments of one vertex array in parallel.
+        Returns (blob u8, offsets u64[n], sizes u64[n]); segment i is blob[offsets[i]:offsets[i]+sizes[i]].
+        Every segment starts on a 16-byte boundary of the blob."""
+        v = _u8(vertices)
+        firsts = np.ascontiguousarray(firsts, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        n = firsts.size
+        caps = np.array([(self.encode_bound(int(c), vertex_size) + 15) & ~15 for c in counts], dtype=np.uint64)
+        offs = np.zeros(n, dtype=np.uint64)
+        np.cumsum(caps[:-1], out=offs[1:])
+        blob = np.empty(int(caps.sum()), dtype=np.uint8)
+        sizes = np.zeros(n, dtype=np.uint64)
+        self.lib.harness_encode_segments(v.ctypes.data, vertex_size, firsts.ctypes.data, counts.ctypes.data, n, level, version,
+                                         blob.ctypes.data, offs.ctypes.data, caps.ctypes.data, sizes.ctypes.data, threads or self.hw_threads())
+        assert (sizes > 0).all()
+        # compact: keep 16-byte alignment of every segment start
+        new_offs = np.zeros(n, dtype=np.uint64)
+        padded = (sizes + np.uint64(15)) & ~np.uint64(15)
+        np.cumsum(padded[:-1], out=new_offs[1:])
+        out = np.zeros(int(padded.sum()) + 16, dtype=np.uint8)
+        for i in range(n):
+            o, s, no = int(offs[i]), int(sizes[i]), int(new_offs[i])
+            out[no : no + s] = blob[o : o + s]
+        return out, new_offs, sizes
+
+    def grid_reorder(self, vertices: np.ndarray, side: int) -> np.ndarray:
+        v = np.ascontiguousarray(vertices).copy()
+        self.lib.harness_grid_reorder(v.ctypes.data, side)
+        return v
+
+    def encode_filter(self, name: str, data: np.ndarray, count: int, stride: int, bits: int, mode: int = 0) -> np.ndarray:
+        src = np.ascontiguousarray(data, dtype=np.float32)
+        out = np.zeros(count * stride, dtype=np.uint8)
+        f = getattr(self.lib, "meshopt_encodeFilter" + name.capitalize())
+        if name == "exp":
+            f(out.ctypes.data, count, stride, bits, src.ctypes.data, mode)
+        else:
+            f(out.ctypes.data, count, stride, bits, src.ctypes.data)
+        return out
+
+
+_port = None
+_ref = None
+
+
+def port() -> _Lib:
+    global _port
+    if _port is None:
+        if not os.path.exists(PORT_SO):
+            build()
+        _port = _Lib(PORT_SO, "oracle_", "port")
+    return _port
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref() -> _Ref:
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libmeshopt_ref.so not built (needs /root/reference at build time)")
+        _ref = _Ref()
+    return _ref
