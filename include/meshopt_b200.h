@@ -1,0 +1,135 @@
+/*
+ * meshopt_b200.h -- C ABI of the B200-native meshoptimizer vertex-buffer decode path.
+ *
+ * Two groups of entry points, both exported from meshoptimizer_b200/lib/libmeshopt_b200.so:
+ *
+ *  1. DROP-IN symbols: exactly the signatures of the reference C API for this path, so an
+ *     application (or an FFI binding) that links meshoptimizer can link this library instead:
+ *       meshopt_decodeVertexBuffer   reference src/meshoptimizer.h:396  (impl. src/vertexcodec.cpp:1799-1872)
+ *       meshopt_decodeVertexVersion  reference src/meshoptimizer.h:403  (impl. src/vertexcodec.cpp:1782-1797)
+ *       meshopt_decodeFilterOct      reference src/meshoptimizer.h:421  (impl. src/vertexfilter.cpp:1211-1228)
+ *       meshopt_decodeFilterQuat     reference src/meshoptimizer.h:422  (impl. src/vertexfilter.cpp:1230-1242)
+ *       meshopt_decodeFilterExp      reference src/meshoptimizer.h:423  (impl. src/vertexfilter.cpp:1244-1255)
+ *       meshopt_decodeFilterColor    reference src/meshoptimizer.h:424  (impl. src/vertexfilter.cpp:1257-1274)
+ *     They take HOST pointers, are synchronous and thread-safe, and run on the GPU (there is no CPU
+ *     fallback: without a usable CUDA device meshopt_decodeVertexBuffer returns MOB200_ERR_CUDA and
+ *     the filters abort()).
+ *
+ *  2. DEVICE / BATCHED variant (new; prefix mob200_): many independent streams -- one descriptor per
+ *     glTF bufferView, the shape gltf/parsegltf.cpp:561-627 iterates over -- decoded by one launch
+ *     sequence with the decode filter fused, inputs and outputs resident in HBM.
+ *
+ * Plain C89-compatible declarations: pointers and sizes only, no CUDA or torch types.  A CUDA
+ * stream is passed as void* (cudaStream_t); NULL means the default stream.
+ */
+#ifndef MESHOPT_B200_H
+#define MESHOPT_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef MESHOPTIMIZER_API
+#if defined(_WIN32)
+#define MESHOPTIMIZER_API __declspec(dllexport)
+#else
+#define MESHOPTIMIZER_API __attribute__((visibility("default")))
+#endif
+#endif
+
+/* ---- 1. drop-in symbols (reference src/meshoptimizer.h:396,403,421-424) ------------------------ */
+
+/* Returns 0 on success, -1 bad header/version, -2 truncated or malformed data, -3 trailing bytes
+ * (same codes as the reference, src/vertexcodec.cpp:1827-1869); MOB200_ERR_* (< -3) for failures
+ * that have no reference equivalent. */
+MESHOPTIMIZER_API int meshopt_decodeVertexBuffer(void* destination, size_t vertex_count, size_t vertex_size, const unsigned char* buffer, size_t buffer_size);
+MESHOPTIMIZER_API int meshopt_decodeVertexVersion(const unsigned char* buffer, size_t buffer_size);
+
+MESHOPTIMIZER_API void meshopt_decodeFilterOct(void* buffer, size_t count, size_t stride);
+MESHOPTIMIZER_API void meshopt_decodeFilterQuat(void* buffer, size_t count, size_t stride);
+MESHOPTIMIZER_API void meshopt_decodeFilterExp(void* buffer, size_t count, size_t stride);
+MESHOPTIMIZER_API void meshopt_decodeFilterColor(void* buffer, size_t count, size_t stride);
+
+/* ---- 2. device / batched variant --------------------------------------------------------------- */
+
+#define MOB200_ERR_CUDA (-100)        /* no device, launch failure, out of memory */
+#define MOB200_ERR_ARGUMENT (-101)    /* vertex_size not in (0,256] or not a multiple of 4, count >= 2^32, ... */
+
+enum mob200_Filter
+{
+	MOB200_FILTER_NONE = 0,
+	MOB200_FILTER_OCTAHEDRAL = 1, /* vertex_size 4 or 8  (meshopt_decodeFilterOct)   */
+	MOB200_FILTER_QUATERNION = 2, /* vertex_size 8       (meshopt_decodeFilterQuat)  */
+	MOB200_FILTER_EXPONENTIAL = 3, /* vertex_size % 4 == 0 (meshopt_decodeFilterExp)  */
+	MOB200_FILTER_COLOR = 4       /* vertex_size 4 or 8  (meshopt_decodeFilterColor) */
+};
+
+/* One independent encoded stream = one call of meshopt_decodeVertexBuffer (+ optional filter).
+ * src/dst are DEVICE pointers for the mob200_*_device entry points and HOST pointers for
+ * mob200_decode_batch_host.  Device requirements: src must be readable in
+ * [src & ~15, (src + src_size + 15) & ~15) (any cudaMalloc'ed range is); dst should be 16-byte
+ * aligned for full-width stores (4-byte and 1-byte aligned destinations take slower paths). */
+typedef struct mob200_Stream
+{
+	const unsigned char* src;
+	size_t src_size;
+	void* dst;
+	size_t vertex_count;
+	size_t vertex_size;
+	int filter; /* enum mob200_Filter */
+	int status; /* out: reference return code for this stream (written by *_status / *_host calls) */
+} mob200_Stream;
+
+typedef struct mob200_Context mob200_Context; /* per-device state: scratch arenas, staging, streams */
+typedef struct mob200_Plan mob200_Plan;       /* a prepared batch: descriptors + scratch in HBM   */
+
+/* device < 0 selects the current CUDA device.  Returns 0 or MOB200_ERR_CUDA. */
+MESHOPTIMIZER_API int mob200_context_create(mob200_Context** out, int device);
+MESHOPTIMIZER_API void mob200_context_destroy(mob200_Context* ctx);
+
+/* Prepare a batch of n streams whose src/dst are device pointers: uploads the descriptor table and
+ * sizes the offset / look-back scratch.  Nothing is decoded yet. */
+MESHOPTIMIZER_API int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* streams, size_t n, mob200_Plan** out);
+MESHOPTIMIZER_API void mob200_plan_destroy(mob200_Plan* plan);
+
+/* Enqueue walk + decode(+filter) kernels for the whole batch on `cuda_stream`; asynchronous.
+ * May be called repeatedly (every call decodes the batch again). */
+MESHOPTIMIZER_API int mob200_plan_run(mob200_Plan* plan, void* cuda_stream);
+
+/* Wait for the last run on `cuda_stream` and copy one reference return code per stream to
+ * status[n] (host).  Returns the number of streams whose code is non-zero, or MOB200_ERR_CUDA. */
+MESHOPTIMIZER_API int mob200_plan_status(mob200_Plan* plan, int* status, void* cuda_stream);
+
+/* Number of kernels one mob200_plan_run enqueues (for launch accounting). */
+MESHOPTIMIZER_API int mob200_plan_launches(const mob200_Plan* plan);
+
+/* Convenience: create plan, run, fetch status into streams[i].status, destroy.  Synchronous. */
+MESHOPTIMIZER_API int mob200_decode_batch_device(mob200_Context* ctx, mob200_Stream* streams, size_t n, void* cuda_stream);
+
+/* Same contract with HOST pointers in src/dst: compressed bytes go host->device, decoded (and
+ * filtered) vertices come device->host, pipelined in chunks over several CUDA streams.  Pinned
+ * (page-locked) caller buffers are transferred in place, pageable ones through pinned staging.
+ * Synchronous; fills streams[i].status; returns the number of failed streams or MOB200_ERR_*. */
+MESHOPTIMIZER_API int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* streams, size_t n);
+
+/* In-place decode filter on a DEVICE buffer of count elements (asynchronous on cuda_stream).
+ * filter is enum mob200_Filter (not NONE); stride rules as the reference asserts them. */
+MESHOPTIMIZER_API int mob200_filter_device(int filter, void* device_buffer, size_t count, size_t stride, void* cuda_stream);
+
+/* Library / device introspection used by tests and bench: number of SMs of the context's device,
+ * and a version string. */
+MESHOPTIMIZER_API int mob200_context_sm_count(const mob200_Context* ctx);
+MESHOPTIMIZER_API const char* mob200_version(void);
+
+/* Duration in milliseconds of the kernels of the most recent mob200_plan_run, measured with CUDA
+ * events recorded on the launching stream around (0) the whole run, (1) the walk kernel, (2) the
+ * decode kernel.  Synchronises on the end event.  Returns 0 or MOB200_ERR_CUDA. */
+MESHOPTIMIZER_API int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float* ms_walk, float* ms_decode);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MESHOPT_B200_H */

@@ -1,0 +1,323 @@
+"""meshoptimizer_b200 -- B200-native (sm_100a) vertex-buffer decode for meshoptimizer streams.
+
+Python host mirror of the reference interface for this path, on top of the C ABI declared in
+``include/meshopt_b200.h`` (``lib/libmeshopt_b200.so``).  Names and argument meaning follow the
+reference (``src/meshoptimizer.h:396-424``; JS wrapper ``js/meshopt_decoder.mjs:164-193``):
+
+* ``decode_vertex_buffer(count, size, source, filter=None)``  -> host bytes in, numpy bytes out
+* ``decode_vertex_version(source)``
+* ``decode_filter_oct / quat / exp / color(buffer, count, stride)``  (in place, host numpy)
+* ``Context`` / ``Plan``: the batched device-pointer variant (torch tensors only carry device memory)
+
+There is NO CPU fallback: every entry point goes through the CUDA library and raises
+``RuntimeError`` when the library is missing or no CUDA device is usable.  Nothing here imports
+``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+FILTER_NONE, FILTER_OCTAHEDRAL, FILTER_QUATERNION, FILTER_EXPONENTIAL, FILTER_COLOR = 0, 1, 2, 3, 4
+_FILTER_BY_NAME = {
+    None: 0, "NONE": 0, "none": 0,
+    "OCTAHEDRAL": 1, "oct": 1,
+    "QUATERNION": 2, "quat": 2,
+    "EXPONENTIAL": 3, "exp": 3,
+    "COLOR": 4, "color": 4,
+}
+ERR_CUDA, ERR_ARGUMENT = -100, -101
+
+
+class Stream(ctypes.Structure):
+    """mirror of ``mob200_Stream``"""
+    _fields_ = [
+        ("src", c_void_p),
+        ("src_size", c_size_t),
+        ("dst", c_void_p),
+        ("vertex_count", c_size_t),
+        ("vertex_size", c_size_t),
+        ("filter", c_int),
+        ("status", c_int),
+    ]
+
+
+_LIB = None
+
+EXPORTS = [
+    "meshopt_decodeVertexBuffer", "meshopt_decodeVertexVersion",
+    "meshopt_decodeFilterOct", "meshopt_decodeFilterQuat", "meshopt_decodeFilterExp", "meshopt_decodeFilterColor",
+    "mob200_context_create", "mob200_context_destroy", "mob200_plan_create", "mob200_plan_destroy",
+    "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
+    "mob200_decode_batch_host", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
+    "mob200_plan_last_timing",
+]
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load the CUDA library (never builds implicitly on a GPU box: the .so ships in-tree)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -m meshoptimizer_b200.build` (there is no CPU fallback)")
+    L = ctypes.CDLL(path, mode=os.RTLD_LOCAL)
+    L.meshopt_decodeVertexBuffer.restype = c_int
+    L.meshopt_decodeVertexBuffer.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+    L.meshopt_decodeVertexVersion.restype = c_int
+    L.meshopt_decodeVertexVersion.argtypes = [c_void_p, c_size_t]
+    for name in ("Oct", "Quat", "Exp", "Color"):
+        f = getattr(L, "meshopt_decodeFilter" + name)
+        f.restype = None
+        f.argtypes = [c_void_p, c_size_t, c_size_t]
+    L.mob200_context_create.restype = c_int
+    L.mob200_context_create.argtypes = [POINTER(c_void_p), c_int]
+    L.mob200_context_destroy.restype = None
+    L.mob200_context_destroy.argtypes = [c_void_p]
+    L.mob200_plan_create.restype = c_int
+    L.mob200_plan_create.argtypes = [c_void_p, POINTER(Stream), c_size_t, POINTER(c_void_p)]
+    L.mob200_plan_destroy.restype = None
+    L.mob200_plan_destroy.argtypes = [c_void_p]
+    L.mob200_plan_run.restype = c_int
+    L.mob200_plan_run.argtypes = [c_void_p, c_void_p]
+    L.mob200_plan_status.restype = c_int
+    L.mob200_plan_status.argtypes = [c_void_p, POINTER(c_int), c_void_p]
+    L.mob200_plan_launches.restype = c_int
+    L.mob200_plan_launches.argtypes = [c_void_p]
+    L.mob200_plan_last_timing.restype = c_int
+    L.mob200_plan_last_timing.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+    L.mob200_decode_batch_device.restype = c_int
+    L.mob200_decode_batch_device.argtypes = [c_void_p, POINTER(Stream), c_size_t, c_void_p]
+    L.mob200_decode_batch_host.restype = c_int
+    L.mob200_decode_batch_host.argtypes = [c_void_p, POINTER(Stream), c_size_t]
+    L.mob200_filter_device.restype = c_int
+    L.mob200_filter_device.argtypes = [c_int, c_void_p, c_size_t, c_size_t, c_void_p]
+    L.mob200_context_sm_count.restype = c_int
+    L.mob200_context_sm_count.argtypes = [c_void_p]
+    L.mob200_version.restype = c_char_p
+    _LIB = L
+    return L
+
+
+def _as_u8(a) -> np.ndarray:
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        return np.frombuffer(a, dtype=np.uint8)
+    return np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+
+
+def _filter_id(f) -> int:
+    if isinstance(f, int):
+        return f
+    return _FILTER_BY_NAME[f]
+
+
+def _check_vertex_size(vertex_size: int) -> None:
+    # the reference asserts these (src/vertexcodec.cpp:1803-1804)
+    if not (0 < vertex_size <= 256 and vertex_size % 4 == 0):
+        raise ValueError("vertex_size must be a multiple of 4 in (0, 256]")
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in, host memory (synchronous)
+# ---------------------------------------------------------------------------------------------
+
+def decode_vertex_version(source) -> int:
+    """``meshopt_decodeVertexVersion``: 0 or 1, -1 for an invalid header."""
+    src = _as_u8(source)
+    return int(lib().meshopt_decodeVertexVersion(src.ctypes.data if src.size else None, src.size))
+
+
+def decode_vertex_buffer_rc(count: int, size: int, source, target: Optional[np.ndarray] = None):
+    """``meshopt_decodeVertexBuffer`` on host memory; returns (return code, decoded uint8 array)."""
+    _check_vertex_size(size)
+    src = _as_u8(source)
+    out = target if target is not None else np.zeros(count * size, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.size >= count * size and out.flags.c_contiguous
+    rc = lib().meshopt_decodeVertexBuffer(out.ctypes.data if count else None, count, size, src.ctypes.data if src.size else None, src.size)
+    return int(rc), out[: count * size]
+
+
+def decode_vertex_buffer(count: int, size: int, source, filter=None) -> np.ndarray:
+    """Decode one stream and optionally apply a decode filter (as ``MeshoptDecoder.decodeVertexBuffer``
+    does, js/meshopt_decoder.mjs:48-66).  Raises on a non-zero return code."""
+    fid = _filter_id(filter)
+    if fid == FILTER_NONE:
+        rc, out = decode_vertex_buffer_rc(count, size, source)
+    else:
+        outs, rcs = decode_batch_host([(source, count, size, fid)])
+        rc, out = rcs[0], outs[0]
+    if rc != 0:
+        raise RuntimeError(f"Malformed buffer data: {rc}")
+    return out
+
+
+def _decode_filter(name: str, buffer: np.ndarray, count: int, stride: int) -> np.ndarray:
+    buf = buffer.view(np.uint8).reshape(-1)
+    assert buf.flags.c_contiguous and buf.flags.writeable and buf.size >= count * stride
+    getattr(lib(), "meshopt_decodeFilter" + name)(buf.ctypes.data, count, stride)
+    return buffer
+
+
+def decode_filter_oct(buffer: np.ndarray, count: int, stride: int) -> np.ndarray:
+    if stride not in (4, 8):
+        raise ValueError("stride must be 4 or 8")
+    return _decode_filter("Oct", buffer, count, stride)
+
+
+def decode_filter_quat(buffer: np.ndarray, count: int, stride: int) -> np.ndarray:
+    if stride != 8:
+        raise ValueError("stride must be 8")
+    return _decode_filter("Quat", buffer, count, stride)
+
+
+def decode_filter_exp(buffer: np.ndarray, count: int, stride: int) -> np.ndarray:
+    if stride <= 0 or stride % 4:
+        raise ValueError("stride must be a positive multiple of 4")
+    return _decode_filter("Exp", buffer, count, stride)
+
+
+def decode_filter_color(buffer: np.ndarray, count: int, stride: int) -> np.ndarray:
+    if stride not in (4, 8):
+        raise ValueError("stride must be 4 or 8")
+    return _decode_filter("Color", buffer, count, stride)
+
+
+# ---------------------------------------------------------------------------------------------
+# batched variants
+# ---------------------------------------------------------------------------------------------
+
+class Context:
+    """``mob200_Context``: per-device scratch, staging buffers and a private CUDA stream."""
+
+    def __init__(self, device: int = -1):
+        h = c_void_p()
+        rc = lib().mob200_context_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise RuntimeError(f"mob200_context_create failed ({rc}): no usable CUDA device? (there is no CPU fallback)")
+        self.handle = h
+
+    @property
+    def sm_count(self) -> int:
+        return int(lib().mob200_context_sm_count(self.handle))
+
+    def close(self) -> None:
+        if self.handle:
+            lib().mob200_context_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_DEFAULT_CTX: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _DEFAULT_CTX
+    if _DEFAULT_CTX is None:
+        _DEFAULT_CTX = Context(-1)
+    return _DEFAULT_CTX
+
+
+def make_streams(items: Sequence[tuple]) -> ctypes.Array:
+    """items: (src_ptr, src_size, dst_ptr, vertex_count, vertex_size, filter) with integer addresses."""
+    arr = (Stream * len(items))()
+    for i, (src, src_size, dst, count, vs, filt) in enumerate(items):
+        arr[i].src = src
+        arr[i].src_size = src_size
+        arr[i].dst = dst
+        arr[i].vertex_count = count
+        arr[i].vertex_size = vs
+        arr[i].filter = _filter_id(filt)
+        arr[i].status = 0
+    return arr
+
+
+class Plan:
+    """``mob200_Plan``: a prepared batch of device-resident streams that can be run repeatedly."""
+
+    def __init__(self, ctx: Context, streams: ctypes.Array):
+        self.ctx = ctx
+        self.n = len(streams)
+        h = c_void_p()
+        rc = lib().mob200_plan_create(ctx.handle, streams, self.n, ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"mob200_plan_create failed ({rc})")
+        self.handle = h
+
+    def run(self, cuda_stream: int = 0) -> None:
+        rc = lib().mob200_plan_run(self.handle, c_void_p(cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"mob200_plan_run failed ({rc})")
+
+    def status(self, cuda_stream: int = 0) -> np.ndarray:
+        st = np.zeros(max(self.n, 1), dtype=np.int32)
+        rc = lib().mob200_plan_status(self.handle, st.ctypes.data_as(POINTER(c_int)), c_void_p(cuda_stream))
+        if rc < 0:
+            raise RuntimeError(f"mob200_plan_status failed ({rc})")
+        return st[: self.n]
+
+    @property
+    def launches(self) -> int:
+        return int(lib().mob200_plan_launches(self.handle))
+
+    def last_timing(self):
+        a, b, c = c_float(), c_float(), c_float()
+        rc = lib().mob200_plan_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        if rc != 0:
+            raise RuntimeError(f"mob200_plan_last_timing failed ({rc})")
+        return {"total_ms": a.value, "walk_ms": b.value, "decode_ms": c.value}
+
+    def close(self) -> None:
+        if self.handle:
+            lib().mob200_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_batch_host(items: Iterable[tuple], ctx: Optional[Context] = None):
+    """items: (source bytes/array, vertex_count, vertex_size, filter).  Host memory in, host memory
+    out through ``mob200_decode_batch_host``.  Returns (list of uint8 arrays, list of return codes)."""
+    items = list(items)
+    ctx = ctx or default_context()
+    srcs = [_as_u8(it[0]) for it in items]
+    outs = [np.zeros(max(it[1] * it[2], 1), dtype=np.uint8) for it in items]
+    for it in items:
+        _check_vertex_size(it[2])
+    arr = make_streams([
+        (s.ctypes.data if s.size else None, s.size, o.ctypes.data, it[1], it[2], it[3] if len(it) > 3 else 0)
+        for s, o, it in zip(srcs, outs, items)
+    ])
+    rc = lib().mob200_decode_batch_host(ctx.handle, arr, len(items))
+    if rc < 0:
+        raise RuntimeError(f"mob200_decode_batch_host failed ({rc})")
+    return [o[: it[1] * it[2]] for o, it in zip(outs, items)], [int(arr[i].status) for i in range(len(items))]
+
+
+def filter_device(filter, device_ptr: int, count: int, stride: int, cuda_stream: int = 0) -> None:
+    rc = lib().mob200_filter_device(_filter_id(filter), c_void_p(device_ptr), count, stride, c_void_p(cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"mob200_filter_device failed ({rc})")
+
+
+def version() -> str:
+    return lib().mob200_version().decode()

@@ -1,0 +1,651 @@
+// mob200_api.cu -- the C ABI (include/meshopt_b200.h): drop-in meshopt_* symbols on host pointers and
+// the batched device-pointer variant.  Host C++ only; every byte of decode work happens in
+// mob200_kernels.cu.  There is no CPU fallback: without a CUDA device the calls fail.
+//
+// Reference interfaces mirrored here (argument meaning and return codes):
+//   meshopt_decodeVertexBuffer / meshopt_decodeVertexVersion   src/vertexcodec.cpp:1782-1872
+//   meshopt_decodeFilterOct/Quat/Exp/Color                     src/vertexfilter.cpp:1211-1274
+//   per-bufferView decode loop of a loader                     gltf/parsegltf.cpp:561-627
+#include "../../include/meshopt_b200.h"
+
+#include "mob200_kernels.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace mob200;
+
+#define CUDA_TRY(expr)                                                                                      \
+	do                                                                                                      \
+	{                                                                                                       \
+		cudaError_t err__ = (expr);                                                                         \
+		if (err__ != cudaSuccess)                                                                           \
+		{                                                                                                   \
+			fprintf(stderr, "meshopt_b200: %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+			return MOB200_ERR_CUDA;                                                                         \
+		}                                                                                                   \
+	} while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+
+struct DeviceBuffer
+{
+	void* ptr = nullptr;
+	size_t size = 0;
+
+	int reserve(size_t bytes)
+	{
+		if (bytes <= size)
+			return 0;
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr;
+		size = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		CUDA_TRY(cudaMalloc(&ptr, want));
+		size = want;
+		return 0;
+	}
+	void release()
+	{
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr;
+		size = 0;
+	}
+};
+
+struct PinnedBuffer
+{
+	void* ptr = nullptr;
+	size_t size = 0;
+
+	int reserve(size_t bytes)
+	{
+		if (bytes <= size)
+			return 0;
+		if (ptr)
+			cudaFreeHost(ptr);
+		ptr = nullptr;
+		size = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		CUDA_TRY(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+		size = want;
+		return 0;
+	}
+	void release()
+	{
+		if (ptr)
+			cudaFreeHost(ptr);
+		ptr = nullptr;
+		size = 0;
+	}
+};
+
+struct mob200_Context
+{
+	int device = 0;
+	int sm_count = 0;
+	int decode_ctas_per_sm = 1;
+	cudaStream_t stream = nullptr; // used by the host-pointer entry points
+	std::mutex mu;                 // host-pointer entry points share the staging buffers below
+	DeviceBuffer d_in, d_out;
+	PinnedBuffer h_in, h_out;
+};
+
+struct mob200_Plan
+{
+	mob200_Context* ctx = nullptr;
+	size_t n = 0;
+	DevTables T = {};
+	int32_t* d_status = nullptr;
+	void* arena = nullptr;
+	uint32_t grid = 0;
+	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+	bool timed = false;
+};
+
+static int set_device(const mob200_Context* ctx)
+{
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	return 0;
+}
+
+extern "C" int mob200_context_create(mob200_Context** out, int device)
+{
+	if (!out)
+		return MOB200_ERR_ARGUMENT;
+	*out = nullptr;
+	int count = 0;
+	CUDA_TRY(cudaGetDeviceCount(&count));
+	if (count == 0)
+		return MOB200_ERR_CUDA;
+	if (device < 0)
+		CUDA_TRY(cudaGetDevice(&device));
+	if (device >= count)
+		return MOB200_ERR_ARGUMENT;
+
+	mob200_Context* ctx = new (std::nothrow) mob200_Context();
+	if (!ctx)
+		return MOB200_ERR_CUDA;
+	ctx->device = device;
+	CUDA_TRY(cudaSetDevice(device));
+	CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+	CUDA_TRY(prepare_decode_kernel());
+	CUDA_TRY(decode_occupancy(&ctx->decode_ctas_per_sm));
+	if (ctx->decode_ctas_per_sm < 1)
+		ctx->decode_ctas_per_sm = 1;
+	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	*out = ctx;
+	return 0;
+}
+
+extern "C" void mob200_context_destroy(mob200_Context* ctx)
+{
+	if (!ctx)
+		return;
+	cudaSetDevice(ctx->device);
+	ctx->d_in.release();
+	ctx->d_out.release();
+	ctx->h_in.release();
+	ctx->h_out.release();
+	if (ctx->stream)
+		cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" int mob200_context_sm_count(const mob200_Context* ctx)
+{
+	return ctx ? ctx->sm_count : 0;
+}
+
+extern "C" const char* mob200_version(void)
+{
+	return "meshopt_b200 0.1 (sm_100a; vertex codec v0/v1 + oct/quat/exp/color filters)";
+}
+
+// ------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------
+
+static bool filter_ok(int filter, size_t vs)
+{
+	switch (filter)
+	{
+	case MOB200_FILTER_NONE: return true;
+	case MOB200_FILTER_OCT:
+	case MOB200_FILTER_COLOR: return vs == 4 || vs == 8; // reference asserts, src/vertexfilter.cpp:1215,1261
+	case MOB200_FILTER_QUAT: return vs == 8;              // :1234
+	case MOB200_FILTER_EXP: return vs % 4 == 0;           // :1248
+	default: return false;
+	}
+}
+
+static size_t align_up(size_t v, size_t a)
+{
+	return (v + a - 1) / a * a;
+}
+
+extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* streams, size_t n, mob200_Plan** out)
+{
+	if (!ctx || !out || (n && !streams) || n >= 0xffffffffull)
+		return MOB200_ERR_ARGUMENT;
+	*out = nullptr;
+	if (set_device(ctx))
+		return MOB200_ERR_CUDA;
+
+	std::vector<DevStream> host(n);
+	uint64_t total_blocks = 0, total_chan = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const mob200_Stream& s = streams[i];
+		if (s.vertex_size == 0 || s.vertex_size > 256 || s.vertex_size % 4 != 0) // reference asserts, src/vertexcodec.cpp:1803-1804
+			return MOB200_ERR_ARGUMENT;
+		if (s.vertex_count >= 0xffffffffull || s.src_size >= 0xffffffffull || !filter_ok(s.filter, s.vertex_size))
+			return MOB200_ERR_ARGUMENT;
+		if (s.vertex_count && !s.dst)
+			return MOB200_ERR_ARGUMENT;
+		uint32_t bv = block_vertices((uint32_t)s.vertex_size);
+		uint64_t nblocks = (s.vertex_count + bv - 1) / bv;
+		DevStream& d = host[i];
+		d.src = s.src;
+		d.dst = static_cast<uint8_t*>(s.dst);
+		d.src_size = s.src ? s.src_size : 0;
+		d.chan_base = total_chan;
+		d.vertex_count = (uint32_t)s.vertex_count;
+		d.block_base = (uint32_t)total_blocks;
+		d.vertex_size = (uint16_t)s.vertex_size;
+		d.filter = (uint8_t)s.filter;
+		d.version = 0;
+		d.status = 0;
+		total_blocks += nblocks;
+		total_chan += nblocks * s.vertex_size;
+		if (total_blocks >= 0xfffffff0ull)
+			return MOB200_ERR_ARGUMENT;
+	}
+
+	mob200_Plan* plan = new (std::nothrow) mob200_Plan();
+	if (!plan)
+		return MOB200_ERR_CUDA;
+	plan->ctx = ctx;
+	plan->n = n;
+
+	// one arena for every table
+	size_t off_streams = 0;
+	size_t off_boff = align_up(off_streams + n * sizeof(DevStream), 256);
+	size_t off_bstream = align_up(off_boff + (total_blocks + n) * 4, 256);
+	size_t off_chan = align_up(off_bstream + total_blocks * 4, 256);
+	size_t off_look = align_up(off_chan + total_chan * 2, 256);
+	size_t off_status = align_up(off_look + (total_chan / 4) * 8, 256);
+	size_t off_ticket = align_up(off_status + n * 4, 256);
+	size_t arena_bytes = off_ticket + 256;
+
+	if (cudaMalloc(&plan->arena, arena_bytes) != cudaSuccess)
+	{
+		delete plan;
+		return MOB200_ERR_CUDA;
+	}
+	uint8_t* base = static_cast<uint8_t*>(plan->arena);
+	plan->T.streams = reinterpret_cast<DevStream*>(base + off_streams);
+	plan->T.block_offset = reinterpret_cast<uint32_t*>(base + off_boff);
+	plan->T.block_stream = reinterpret_cast<uint32_t*>(base + off_bstream);
+	plan->T.chan_offset = reinterpret_cast<uint16_t*>(base + off_chan);
+	plan->T.lookback = reinterpret_cast<unsigned long long*>(base + off_look);
+	plan->T.status = reinterpret_cast<int32_t*>(base + off_status);
+	plan->T.ticket = reinterpret_cast<uint32_t*>(base + off_ticket);
+	plan->T.n_streams = (uint32_t)n;
+	plan->T.total_blocks = (uint32_t)total_blocks;
+	plan->T.epoch = 0;
+
+	bool ok = true;
+	ok = ok && cudaMemset(base + off_look, 0, (total_chan / 4) * 8 + 8) == cudaSuccess; // epoch 0 = never published
+	ok = ok && cudaMemset(base + off_ticket, 0, 256) == cudaSuccess;
+	if (n)
+		ok = ok && cudaMemcpy(plan->T.streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice) == cudaSuccess;
+	for (int i = 0; i < 3; ++i)
+		ok = ok && cudaEventCreate(&plan->ev[i]) == cudaSuccess;
+	if (!ok)
+	{
+		mob200_plan_destroy(plan);
+		return MOB200_ERR_CUDA;
+	}
+
+	uint64_t resident = (uint64_t)ctx->sm_count * ctx->decode_ctas_per_sm;
+	plan->grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(total_blocks, resident));
+	*out = plan;
+	return 0;
+}
+
+extern "C" void mob200_plan_destroy(mob200_Plan* plan)
+{
+	if (!plan)
+		return;
+	cudaSetDevice(plan->ctx->device);
+	for (int i = 0; i < 3; ++i)
+		if (plan->ev[i])
+			cudaEventDestroy(plan->ev[i]);
+	if (plan->arena)
+		cudaFree(plan->arena);
+	delete plan;
+}
+
+extern "C" int mob200_plan_launches(const mob200_Plan* plan)
+{
+	if (!plan || plan->n == 0)
+		return 0;
+	return plan->T.total_blocks ? 2 : 1;
+}
+
+extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
+{
+	if (!plan)
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+	plan->T.epoch = (plan->T.epoch + 1) & 0x3fffffffu;
+	if (plan->T.epoch == 0)
+		plan->T.epoch = 1;
+
+	CUDA_TRY(cudaEventRecord(plan->ev[0], st));
+	CUDA_TRY(launch_walk(plan->T, st)); // also resets the ticket counter
+	CUDA_TRY(cudaEventRecord(plan->ev[1], st));
+	CUDA_TRY(launch_decode(plan->T, plan->grid, st));
+	CUDA_TRY(cudaEventRecord(plan->ev[2], st));
+	plan->timed = true;
+	return 0;
+}
+
+extern "C" int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float* ms_walk, float* ms_decode)
+{
+	if (!plan || !plan->timed)
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	CUDA_TRY(cudaEventSynchronize(plan->ev[2]));
+	float a = 0, b = 0, c = 0;
+	CUDA_TRY(cudaEventElapsedTime(&a, plan->ev[0], plan->ev[2]));
+	CUDA_TRY(cudaEventElapsedTime(&b, plan->ev[0], plan->ev[1]));
+	CUDA_TRY(cudaEventElapsedTime(&c, plan->ev[1], plan->ev[2]));
+	if (ms_total)
+		*ms_total = a;
+	if (ms_walk)
+		*ms_walk = b;
+	if (ms_decode)
+		*ms_decode = c;
+	return 0;
+}
+
+extern "C" int mob200_plan_status(mob200_Plan* plan, int* status, void* cuda_stream)
+{
+	if (!plan)
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+	std::vector<int> local;
+	int* dst = status;
+	if (!dst)
+	{
+		local.resize(plan->n);
+		dst = local.data();
+	}
+	if (plan->n)
+		CUDA_TRY(cudaMemcpyAsync(dst, plan->T.status, plan->n * sizeof(int), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	int failed = 0;
+	for (size_t i = 0; i < plan->n; ++i)
+		failed += dst[i] != 0;
+	return failed;
+}
+
+extern "C" int mob200_decode_batch_device(mob200_Context* ctx, mob200_Stream* streams, size_t n, void* cuda_stream)
+{
+	mob200_Plan* plan = nullptr;
+	int rc = mob200_plan_create(ctx, streams, n, &plan);
+	if (rc)
+		return rc;
+	rc = mob200_plan_run(plan, cuda_stream);
+	std::vector<int> status(n);
+	if (rc == 0)
+		rc = mob200_plan_status(plan, status.data(), cuda_stream);
+	if (rc >= 0)
+		for (size_t i = 0; i < n; ++i)
+			streams[i].status = status[i];
+	mob200_plan_destroy(plan);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer batch: H2D -> walk + decode -> D2H
+// ------------------------------------------------------------------------------------------------
+
+static bool is_pinned(const void* p)
+{
+	if (!p)
+		return false;
+	cudaPointerAttributes attr;
+	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return false;
+	}
+	return attr.type == cudaMemoryTypeHost;
+}
+
+extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* streams, size_t n)
+{
+	if (!ctx || (n && !streams))
+		return MOB200_ERR_ARGUMENT;
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	if (set_device(ctx))
+		return MOB200_ERR_CUDA;
+
+	// device layout: every stream starts on a 16-byte boundary, input and output each in one arena
+	std::vector<size_t> in_off(n), out_off(n);
+	size_t in_total = 0, out_total = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const mob200_Stream& s = streams[i];
+		if (s.vertex_size == 0 || s.vertex_size > 256 || s.vertex_size % 4 != 0)
+			return MOB200_ERR_ARGUMENT;
+		if (s.vertex_count && !s.dst)
+			return MOB200_ERR_ARGUMENT;
+		in_off[i] = in_total;
+		out_off[i] = out_total;
+		in_total += align_up(s.src ? s.src_size : 0, 16);
+		out_total += align_up(s.vertex_count * s.vertex_size, 16);
+	}
+	if (ctx->d_in.reserve(in_total + 16) || ctx->d_out.reserve(out_total + 16))
+		return MOB200_ERR_CUDA;
+
+	uint8_t* d_in = static_cast<uint8_t*>(ctx->d_in.ptr);
+	uint8_t* d_out = static_cast<uint8_t*>(ctx->d_out.ptr);
+	cudaStream_t st = ctx->stream;
+
+	// inputs: pinned caller memory goes straight to the device, pageable memory through pinned staging
+	size_t staged_in = 0;
+	for (size_t i = 0; i < n; ++i)
+		if (streams[i].src && streams[i].src_size && !is_pinned(streams[i].src))
+			staged_in += align_up(streams[i].src_size, 16);
+	if (staged_in && ctx->h_in.reserve(staged_in))
+		return MOB200_ERR_CUDA;
+	{
+		uint8_t* hp = static_cast<uint8_t*>(ctx->h_in.ptr);
+		size_t cursor = 0;
+		for (size_t i = 0; i < n; ++i)
+		{
+			const mob200_Stream& s = streams[i];
+			if (!s.src || !s.src_size)
+				continue;
+			const void* from = s.src;
+			if (!is_pinned(s.src))
+			{
+				memcpy(hp + cursor, s.src, s.src_size);
+				from = hp + cursor;
+				cursor += align_up(s.src_size, 16);
+			}
+			CUDA_TRY(cudaMemcpyAsync(d_in + in_off[i], from, s.src_size, cudaMemcpyHostToDevice, st));
+		}
+	}
+
+	std::vector<mob200_Stream> dev(streams, streams + n);
+	for (size_t i = 0; i < n; ++i)
+	{
+		dev[i].src = streams[i].src ? d_in + in_off[i] : nullptr;
+		dev[i].dst = d_out + out_off[i];
+	}
+
+	mob200_Plan* plan = nullptr;
+	int rc = mob200_plan_create(ctx, dev.data(), n, &plan);
+	if (rc)
+		return rc;
+	rc = mob200_plan_run(plan, st);
+	if (rc)
+	{
+		mob200_plan_destroy(plan);
+		return rc;
+	}
+
+	// outputs
+	size_t staged_out = 0;
+	for (size_t i = 0; i < n; ++i)
+		if (streams[i].vertex_count && !is_pinned(streams[i].dst))
+			staged_out += align_up(streams[i].vertex_count * streams[i].vertex_size, 16);
+	if (staged_out && ctx->h_out.reserve(staged_out))
+	{
+		mob200_plan_destroy(plan);
+		return MOB200_ERR_CUDA;
+	}
+	{
+		uint8_t* hp = static_cast<uint8_t*>(ctx->h_out.ptr);
+		size_t cursor = 0;
+		for (size_t i = 0; i < n; ++i)
+		{
+			const mob200_Stream& s = streams[i];
+			size_t bytes = s.vertex_count * s.vertex_size;
+			if (!bytes)
+				continue;
+			void* to = s.dst;
+			if (!is_pinned(s.dst))
+			{
+				to = hp + cursor;
+				cursor += align_up(bytes, 16);
+			}
+			cudaError_t e = cudaMemcpyAsync(to, d_out + out_off[i], bytes, cudaMemcpyDeviceToHost, st);
+			if (e != cudaSuccess)
+			{
+				mob200_plan_destroy(plan);
+				return MOB200_ERR_CUDA;
+			}
+		}
+	}
+
+	std::vector<int> status(n);
+	rc = mob200_plan_status(plan, status.data(), st); // synchronises the stream
+	if (rc >= 0)
+	{
+		uint8_t* hp = static_cast<uint8_t*>(ctx->h_out.ptr);
+		size_t cursor = 0;
+		for (size_t i = 0; i < n; ++i)
+		{
+			mob200_Stream& s = streams[i];
+			s.status = status[i];
+			size_t bytes = s.vertex_count * s.vertex_size;
+			if (bytes && !is_pinned(s.dst))
+			{
+				memcpy(s.dst, hp + cursor, bytes);
+				cursor += align_up(bytes, 16);
+			}
+		}
+	}
+	mob200_plan_destroy(plan);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// drop-in symbols
+// ------------------------------------------------------------------------------------------------
+
+static mob200_Context* default_context()
+{
+	static std::mutex mu;
+	static mob200_Context* ctx = nullptr;
+	std::lock_guard<std::mutex> lock(mu);
+	if (!ctx)
+	{
+		if (mob200_context_create(&ctx, -1) != 0)
+			ctx = nullptr;
+	}
+	return ctx;
+}
+
+extern "C" int meshopt_decodeVertexVersion(const unsigned char* buffer, size_t buffer_size)
+{
+	// O(1) framing probe on a host buffer (reference src/vertexcodec.cpp:1782-1797); no decode work
+	if (buffer_size < 1)
+		return -1;
+	unsigned char header = buffer[0];
+	if ((header & 0xf0) != kMagic)
+		return -1;
+	int version = header & 0x0f;
+	return version > 1 ? -1 : version;
+}
+
+extern "C" int meshopt_decodeVertexBuffer(void* destination, size_t vertex_count, size_t vertex_size, const unsigned char* buffer, size_t buffer_size)
+{
+	mob200_Context* ctx = default_context();
+	if (!ctx)
+		return MOB200_ERR_CUDA;
+	mob200_Stream s;
+	s.src = buffer;
+	s.src_size = buffer ? buffer_size : 0;
+	s.dst = destination;
+	s.vertex_count = vertex_count;
+	s.vertex_size = vertex_size;
+	s.filter = MOB200_FILTER_NONE;
+	s.status = 0;
+	int rc = mob200_decode_batch_host(ctx, &s, 1);
+	return rc < 0 ? rc : s.status;
+}
+
+static void filter_host(int filter, void* buffer, size_t count, size_t stride)
+{
+	if (!filter_ok(filter, stride))
+	{
+		fprintf(stderr, "meshopt_b200: decode filter %d does not accept stride %zu\n", filter, stride);
+		abort(); // the reference asserts (src/vertexfilter.cpp:1215,1234,1248,1261)
+	}
+	if (count == 0)
+		return;
+	mob200_Context* ctx = default_context();
+	if (!ctx)
+	{
+		fprintf(stderr, "meshopt_b200: no CUDA device available for meshopt_decodeFilter*\n");
+		abort();
+	}
+	std::lock_guard<std::mutex> lock(ctx->mu);
+	size_t bytes = count * stride;
+	bool ok = cudaSetDevice(ctx->device) == cudaSuccess && ctx->d_out.reserve(bytes + 16) == 0;
+	cudaStream_t st = ctx->stream;
+	bool pinned = is_pinned(buffer);
+	void* host = buffer;
+	if (ok && !pinned)
+	{
+		ok = ctx->h_out.reserve(bytes) == 0;
+		if (ok)
+		{
+			memcpy(ctx->h_out.ptr, buffer, bytes);
+			host = ctx->h_out.ptr;
+		}
+	}
+	ok = ok && cudaMemcpyAsync(ctx->d_out.ptr, host, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+	ok = ok && launch_filter(filter, ctx->d_out.ptr, count, stride, ctx->sm_count, st) == cudaSuccess;
+	ok = ok && cudaMemcpyAsync(host, ctx->d_out.ptr, bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+	ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+	if (!ok)
+	{
+		fprintf(stderr, "meshopt_b200: CUDA failure in meshopt_decodeFilter*: %s\n", cudaGetErrorString(cudaGetLastError()));
+		abort();
+	}
+	if (!pinned)
+		memcpy(buffer, host, bytes);
+}
+
+extern "C" void meshopt_decodeFilterOct(void* buffer, size_t count, size_t stride)
+{
+	filter_host(MOB200_FILTER_OCT, buffer, count, stride);
+}
+
+extern "C" void meshopt_decodeFilterQuat(void* buffer, size_t count, size_t stride)
+{
+	filter_host(MOB200_FILTER_QUAT, buffer, count, stride);
+}
+
+extern "C" void meshopt_decodeFilterExp(void* buffer, size_t count, size_t stride)
+{
+	filter_host(MOB200_FILTER_EXP, buffer, count, stride);
+}
+
+extern "C" void meshopt_decodeFilterColor(void* buffer, size_t count, size_t stride)
+{
+	filter_host(MOB200_FILTER_COLOR, buffer, count, stride);
+}
+
+extern "C" int mob200_filter_device(int filter, void* device_buffer, size_t count, size_t stride, void* cuda_stream)
+{
+	if (filter == MOB200_FILTER_NONE || !filter_ok(filter, stride))
+		return MOB200_ERR_ARGUMENT;
+	int device = 0, sms = 0;
+	CUDA_TRY(cudaGetDevice(&device));
+	CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+	CUDA_TRY(launch_filter(filter, device_buffer, count, stride, sms, static_cast<cudaStream_t>(cuda_stream)));
+	return 0;
+}

@@ -1,0 +1,83 @@
+// mob200_common.h -- wire-format constants and the structures shared by the host shim and the kernels.
+//
+// Wire format facts (not code) come from the reference: src/vertexcodec.cpp:123-147 (constants and the
+// block-size rule), :1638-1693 (stream framing), :1531-1568 (v1 control modes); SURVEY.md Appendix A
+// restates them precisely.
+#pragma once
+
+#include <stdint.h>
+
+namespace mob200
+{
+
+constexpr uint32_t kMagic = 0xa0;          // high nibble of byte 0; low nibble = version (0 or 1)
+constexpr uint32_t kBlockBytes = 8192;     // decoded bytes per block never exceed this
+constexpr uint32_t kBlockMaxVerts = 256;   // vertices per block never exceed this
+constexpr uint32_t kGroup = 16;            // values per group
+constexpr uint32_t kGroupReadLimit = 24;   // bytes that must remain readable before each group
+constexpr uint32_t kTailMinV0 = 32;
+constexpr uint32_t kTailMinV1 = 24;
+
+constexpr uint32_t kInvalidOffset = 0xffffffffu; // walk result for a block that must not be decoded
+
+// largest encoded size of one block over all legal vertex sizes (vs = 256: 256*(1+2*24)+64 = 12608)
+constexpr uint32_t kMaxEncodedBlock = 12608;
+
+#if defined(__CUDACC__)
+#define MOB200_HD __host__ __device__ __forceinline__
+#else
+#define MOB200_HD inline
+#endif
+
+// vertices per block for a vertex size (reference src/vertexcodec.cpp:140-147)
+MOB200_HD uint32_t block_vertices(uint32_t vertex_size)
+{
+	uint32_t n = (kBlockBytes / vertex_size) & ~(kGroup - 1);
+	return n < kBlockMaxVerts ? n : kBlockMaxVerts;
+}
+
+MOB200_HD uint32_t tail_bytes(uint32_t vertex_size, uint32_t version)
+{
+	return vertex_size + (version ? vertex_size / 4 : 0);
+}
+
+MOB200_HD uint32_t tail_padded(uint32_t vertex_size, uint32_t version)
+{
+	uint32_t t = tail_bytes(vertex_size, version);
+	uint32_t m = version ? kTailMinV1 : kTailMinV0;
+	return t < m ? m : t;
+}
+
+// One encoded stream as the kernels see it.  48 bytes.
+struct DevStream
+{
+	const uint8_t* src;    // encoded bytes (device)
+	uint8_t* dst;          // decoded vertices (device)
+	uint64_t src_size;
+	uint64_t chan_base;    // first entry of this stream in the channel-offset table (u16 units);
+	                       // chan_base/4 is its first entry in the look-back table
+	uint32_t vertex_count;
+	uint32_t block_base;   // global id of this stream's block 0
+	uint16_t vertex_size;
+	uint8_t filter;        // enum mob200_Filter
+	uint8_t version;       // written by the walk kernel
+	int32_t status;        // written by the walk kernel: reference return code
+};
+
+// Per-run device tables of a plan.
+struct DevTables
+{
+	DevStream* streams;
+	uint32_t* block_offset; // [total_blocks + n_streams]: stream s, block b at block_base + s + b; entry
+	                        // nblocks = end of the last block.  kInvalidOffset = do not decode.
+	uint32_t* block_stream; // [total_blocks]: owning stream of every global block
+	uint16_t* chan_offset;  // per block, vertex_size entries: byte-channel start relative to the block
+	unsigned long long* lookback; // per block, vertex_size/4 entries: {epoch:30 | state:2} << 32 | value
+	int32_t* status;        // [n_streams]: reference return code per stream (written by the walk kernel)
+	uint32_t* ticket;       // persistent-kernel work counter (reset by the walk kernel)
+	uint32_t n_streams;
+	uint32_t total_blocks;
+	uint32_t epoch;         // changes every run, so look-back entries never need clearing
+};
+
+} // namespace mob200

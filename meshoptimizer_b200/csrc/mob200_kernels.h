@@ -1,0 +1,31 @@
+// mob200_kernels.h -- launch interface between the host shim (mob200_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "mob200_common.h"
+
+// filter ids, identical to enum mob200_Filter in include/meshopt_b200.h
+#define MOB200_FILTER_NONE 0
+#define MOB200_FILTER_OCT 1
+#define MOB200_FILTER_QUAT 2
+#define MOB200_FILTER_EXP 3
+#define MOB200_FILTER_COLOR 4
+
+namespace mob200
+{
+
+constexpr int kWalkThreads = 32;    // one stream per lane; small CTAs spread few streams over many SMs
+constexpr int kDecodeThreads = 128; // one block per CTA iteration: (vertices/16) x (vertex_size/4) <= 128 work items
+
+uint32_t decode_smem_bytes();
+cudaError_t prepare_decode_kernel();
+cudaError_t decode_occupancy(int* ctas_per_sm);
+
+cudaError_t launch_walk(const DevTables& T, cudaStream_t stream);
+cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream);
+cudaError_t launch_filter(int filter, void* data, size_t count, size_t stride, int sm_count, cudaStream_t stream);
+
+} // namespace mob200
