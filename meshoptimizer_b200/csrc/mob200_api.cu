@@ -264,11 +264,15 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	plan->T.total_blocks = (uint32_t)total_blocks;
 	plan->T.epoch = 0;
 
+	// table initialisation is enqueued on the context's stream and waited for, so that a later
+	// mob200_plan_run on any stream sees it (cudaMemset on device memory may return early)
 	bool ok = true;
-	ok = ok && cudaMemset(base + off_look, 0, (total_chan / 4) * 8 + 8) == cudaSuccess; // epoch 0 = never published
-	ok = ok && cudaMemset(base + off_ticket, 0, 256) == cudaSuccess;
+	cudaStream_t st = ctx->stream;
+	ok = ok && cudaMemsetAsync(base + off_look, 0, (total_chan / 4) * 8, st) == cudaSuccess; // epoch 0 = never published
+	ok = ok && cudaMemsetAsync(base + off_ticket, 0, 256, st) == cudaSuccess;
 	if (n)
-		ok = ok && cudaMemcpy(plan->T.streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice) == cudaSuccess;
+		ok = ok && cudaMemcpyAsync(plan->T.streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice, st) == cudaSuccess;
+	ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
 	for (int i = 0; i < 3; ++i)
 		ok = ok && cudaEventCreate(&plan->ev[i]) == cudaSuccess;
 	if (!ok)
