@@ -128,6 +128,11 @@ MESHOPTIMIZER_API const char* mob200_version(void);
  * decode kernel.  Synchronises on the end event.  Returns 0 or MOB200_ERR_CUDA. */
 MESHOPTIMIZER_API int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float* ms_walk, float* ms_decode);
 
+/* Same for the most recent runs (at most 64 are remembered, oldest first): fills up to max_runs
+ * entries of each non-NULL array and returns how many were written.  Nothing is synchronised until
+ * this call, so a timed region of repeated mob200_plan_run calls stays asynchronous. */
+MESHOPTIMIZER_API int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms_total, float* ms_walk, float* ms_decode);
+
 #ifdef __cplusplus
 }
 #endif

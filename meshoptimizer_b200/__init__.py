@@ -56,7 +56,7 @@ EXPORTS = [
     "mob200_context_create", "mob200_context_destroy", "mob200_plan_create", "mob200_plan_destroy",
     "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
     "mob200_decode_batch_host", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
-    "mob200_plan_last_timing",
+    "mob200_plan_last_timing", "mob200_plan_timing_history",
 ]
 
 
@@ -97,6 +97,8 @@ def lib() -> ctypes.CDLL:
     L.mob200_plan_launches.argtypes = [c_void_p]
     L.mob200_plan_last_timing.restype = c_int
     L.mob200_plan_last_timing.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+    L.mob200_plan_timing_history.restype = c_int
+    L.mob200_plan_timing_history.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
     L.mob200_decode_batch_device.restype = c_int
     L.mob200_decode_batch_device.argtypes = [c_void_p, POINTER(Stream), c_size_t, c_void_p]
     L.mob200_decode_batch_host.restype = c_int
@@ -281,6 +283,14 @@ class Plan:
         if rc != 0:
             raise RuntimeError(f"mob200_plan_last_timing failed ({rc})")
         return {"total_ms": a.value, "walk_ms": b.value, "decode_ms": c.value}
+
+    def timing_history(self, max_runs: int = 64):
+        """per-run kernel durations (ms) of the most recent runs, oldest first"""
+        a, b, c = (c_float * max_runs)(), (c_float * max_runs)(), (c_float * max_runs)()
+        n = lib().mob200_plan_timing_history(self.handle, max_runs, a, b, c)
+        if n < 0:
+            raise RuntimeError(f"mob200_plan_timing_history failed ({n})")
+        return [{"total_ms": a[i], "walk_ms": b[i], "decode_ms": c[i]} for i in range(n)]
 
     def close(self) -> None:
         if self.handle:

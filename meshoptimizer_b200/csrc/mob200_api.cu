@@ -108,8 +108,12 @@ struct mob200_Plan
 	int32_t* d_status = nullptr;
 	void* arena = nullptr;
 	uint32_t grid = 0;
-	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-	bool timed = false;
+	// ring of CUDA-event triples (before walk, between, after decode), one per run, recorded on the
+	// launching stream: per-kernel durations can be read back after a timed region without any
+	// synchronisation inside it
+	static const int kRing = 64;
+	cudaEvent_t ev[kRing][3] = {};
+	unsigned long long runs = 0;
 };
 
 static int set_device(const mob200_Context* ctx)
@@ -273,8 +277,9 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	if (n)
 		ok = ok && cudaMemcpyAsync(plan->T.streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice, st) == cudaSuccess;
 	ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
-	for (int i = 0; i < 3; ++i)
-		ok = ok && cudaEventCreate(&plan->ev[i]) == cudaSuccess;
+	for (int r = 0; r < mob200_Plan::kRing; ++r)
+		for (int i = 0; i < 3; ++i)
+			ok = ok && cudaEventCreate(&plan->ev[r][i]) == cudaSuccess;
 	if (!ok)
 	{
 		mob200_plan_destroy(plan);
@@ -292,9 +297,10 @@ extern "C" void mob200_plan_destroy(mob200_Plan* plan)
 	if (!plan)
 		return;
 	cudaSetDevice(plan->ctx->device);
-	for (int i = 0; i < 3; ++i)
-		if (plan->ev[i])
-			cudaEventDestroy(plan->ev[i]);
+	for (int r = 0; r < mob200_Plan::kRing; ++r)
+		for (int i = 0; i < 3; ++i)
+			if (plan->ev[r][i])
+				cudaEventDestroy(plan->ev[r][i]);
 	if (plan->arena)
 		cudaFree(plan->arena);
 	delete plan;
@@ -318,33 +324,48 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 	if (plan->T.epoch == 0)
 		plan->T.epoch = 1;
 
-	CUDA_TRY(cudaEventRecord(plan->ev[0], st));
+	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
+	CUDA_TRY(cudaEventRecord(ev[0], st));
 	CUDA_TRY(launch_walk(plan->T, st)); // also resets the ticket counter
-	CUDA_TRY(cudaEventRecord(plan->ev[1], st));
+	CUDA_TRY(cudaEventRecord(ev[1], st));
 	CUDA_TRY(launch_decode(plan->T, plan->grid, st));
-	CUDA_TRY(cudaEventRecord(plan->ev[2], st));
-	plan->timed = true;
+	CUDA_TRY(cudaEventRecord(ev[2], st));
+	plan->runs++;
 	return 0;
+}
+
+extern "C" int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms_total, float* ms_walk, float* ms_decode)
+{
+	if (!plan || max_runs < 0)
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	unsigned long long have = plan->runs < (unsigned long long)mob200_Plan::kRing ? plan->runs : (unsigned long long)mob200_Plan::kRing;
+	int count = (int)(have < (unsigned long long)max_runs ? have : (unsigned long long)max_runs);
+	for (int i = 0; i < count; ++i)
+	{
+		// i = 0 is the oldest of the `count` most recent runs
+		unsigned long long run = plan->runs - count + i;
+		cudaEvent_t* ev = plan->ev[run % mob200_Plan::kRing];
+		CUDA_TRY(cudaEventSynchronize(ev[2]));
+		float a = 0, b = 0, c = 0;
+		CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[2]));
+		CUDA_TRY(cudaEventElapsedTime(&b, ev[0], ev[1]));
+		CUDA_TRY(cudaEventElapsedTime(&c, ev[1], ev[2]));
+		if (ms_total)
+			ms_total[i] = a;
+		if (ms_walk)
+			ms_walk[i] = b;
+		if (ms_decode)
+			ms_decode[i] = c;
+	}
+	return count;
 }
 
 extern "C" int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float* ms_walk, float* ms_decode)
 {
-	if (!plan || !plan->timed)
-		return MOB200_ERR_ARGUMENT;
-	if (set_device(plan->ctx))
-		return MOB200_ERR_CUDA;
-	CUDA_TRY(cudaEventSynchronize(plan->ev[2]));
-	float a = 0, b = 0, c = 0;
-	CUDA_TRY(cudaEventElapsedTime(&a, plan->ev[0], plan->ev[2]));
-	CUDA_TRY(cudaEventElapsedTime(&b, plan->ev[0], plan->ev[1]));
-	CUDA_TRY(cudaEventElapsedTime(&c, plan->ev[1], plan->ev[2]));
-	if (ms_total)
-		*ms_total = a;
-	if (ms_walk)
-		*ms_walk = b;
-	if (ms_decode)
-		*ms_decode = c;
-	return 0;
+	int n = mob200_plan_timing_history(plan, 1, ms_total, ms_walk, ms_decode);
+	return n == 1 ? 0 : (n < 0 ? n : MOB200_ERR_ARGUMENT);
 }
 
 extern "C" int mob200_plan_status(mob200_Plan* plan, int* status, void* cuda_stream)
