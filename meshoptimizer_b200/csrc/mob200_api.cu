@@ -94,6 +94,7 @@ struct mob200_Context
 	int device = 0;
 	int sm_count = 0;
 	int decode_ctas_per_sm = 1;
+	uint32_t walker_lead = 0;      // see DevTables::walker_lead (0 = walkers run unthrottled)
 	cudaStream_t stream = nullptr; // used by the host-pointer entry points
 	std::mutex mu;                 // host-pointer entry points share the staging buffers below
 	DeviceBuffer d_in, d_out;
@@ -147,6 +148,8 @@ extern "C" int mob200_context_create(mob200_Context** out, int device)
 	if (ctx->decode_ctas_per_sm < 1)
 		ctx->decode_ctas_per_sm = 1;
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	if (const char* lead = getenv("MOB200_WALKER_LEAD"))
+		ctx->walker_lead = (uint32_t)strtoul(lead, nullptr, 10);
 	*out = ctx;
 	return 0;
 }
@@ -205,8 +208,9 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	if (set_device(ctx))
 		return MOB200_ERR_CUDA;
 
-	std::vector<DevStream> host(n);
-	uint64_t total_blocks = 0, total_chan = 0;
+	// validate, and sort by block count (descending; ties by vertex size) so that the 32 lanes of a
+	// walker warp advance streams of similar shape and every decode level is a prefix of the array
+	std::vector<uint32_t> nblocks(n);
 	for (size_t i = 0; i < n; ++i)
 	{
 		const mob200_Stream& s = streams[i];
@@ -217,20 +221,36 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 		if (s.vertex_count && !s.dst)
 			return MOB200_ERR_ARGUMENT;
 		uint32_t bv = block_vertices((uint32_t)s.vertex_size);
-		uint64_t nblocks = (s.vertex_count + bv - 1) / bv;
+		nblocks[i] = (uint32_t)((s.vertex_count + bv - 1) / bv);
+	}
+	std::vector<uint32_t> order(n);
+	for (size_t i = 0; i < n; ++i)
+		order[i] = (uint32_t)i;
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+		if (nblocks[a] != nblocks[b])
+			return nblocks[a] > nblocks[b];
+		return streams[a].vertex_size < streams[b].vertex_size;
+	});
+
+	std::vector<DevStream> host(n);
+	uint64_t total_blocks = 0, total_chan = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const mob200_Stream& s = streams[order[i]];
 		DevStream& d = host[i];
 		d.src = s.src;
 		d.dst = static_cast<uint8_t*>(s.dst);
-		d.src_size = s.src ? s.src_size : 0;
 		d.chan_base = total_chan;
+		d.src_size = s.src ? (uint32_t)s.src_size : 0;
 		d.vertex_count = (uint32_t)s.vertex_count;
 		d.block_base = (uint32_t)total_blocks;
+		d.nblocks = nblocks[order[i]];
 		d.vertex_size = (uint16_t)s.vertex_size;
 		d.filter = (uint8_t)s.filter;
-		d.version = 0;
-		d.status = 0;
-		total_blocks += nblocks;
-		total_chan += nblocks * s.vertex_size;
+		d.reserved = 0;
+		d.caller_index = order[i];
+		total_blocks += d.nblocks;
+		total_chan += (uint64_t)d.nblocks * s.vertex_size;
 		if (total_blocks >= 0xfffffff0ull)
 			return MOB200_ERR_ARGUMENT;
 	}
@@ -241,41 +261,83 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	plan->ctx = ctx;
 	plan->n = n;
 
+	uint64_t resident = (uint64_t)ctx->sm_count * ctx->decode_ctas_per_sm;
+	uint64_t wanted = std::max<uint64_t>(total_blocks, (n + 31) / 32);
+	plan->grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(wanted, resident));
+
+	// decode order: streams are walked in waves of grid*32 (one lane each); inside a wave the decoders
+	// take block b of every stream before block b+1 of any, which is the order the walkers produce them
+	std::vector<uint2> ticket_info(total_blocks);
+	std::vector<uint32_t> block_ticket(total_blocks);
+	{
+		const size_t wave = (size_t)plan->grid * 32;
+		size_t t = 0;
+		for (size_t w0 = 0; w0 < n; w0 += wave)
+		{
+			size_t w1 = std::min(n, w0 + wave);
+			uint32_t levels = host[w0].nblocks; // sorted: the first stream of the wave is the longest
+			size_t live = w1 - w0;
+			for (uint32_t b = 0; b < levels; ++b)
+			{
+				while (live > 0 && host[w0 + live - 1].nblocks <= b)
+					--live;
+				for (size_t i = 0; i < live; ++i)
+				{
+					ticket_info[t] = make_uint2((uint32_t)(w0 + i), b);
+					block_ticket[host[w0 + i].block_base + b] = (uint32_t)t;
+					++t;
+				}
+			}
+		}
+	}
+
 	// one arena for every table
 	size_t off_streams = 0;
 	size_t off_boff = align_up(off_streams + n * sizeof(DevStream), 256);
-	size_t off_bstream = align_up(off_boff + (total_blocks + n) * 4, 256);
-	size_t off_chan = align_up(off_bstream + total_blocks * 4, 256);
-	size_t off_look = align_up(off_chan + total_chan * 2, 256);
-	size_t off_status = align_up(off_look + (total_chan / 4) * 8, 256);
-	size_t off_ticket = align_up(off_status + n * 4, 256);
-	size_t arena_bytes = off_ticket + 256;
+	size_t off_table = align_up(off_boff + (total_blocks + n) * 4, 256);
+	size_t off_progress = align_up(off_table + total_chan * 32, 256);
+	size_t off_look = align_up(off_progress + n * 8, 256);
+	size_t off_tinfo = align_up(off_look + (total_chan / 4) * 8, 256);
+	size_t off_bticket = align_up(off_tinfo + total_blocks * 8, 256);
+	size_t off_status = align_up(off_bticket + total_blocks * 4, 256);
+	size_t off_counters = align_up(off_status + n * 4, 256);
+	size_t arena_bytes = off_counters + 256;
 
 	if (cudaMalloc(&plan->arena, arena_bytes) != cudaSuccess)
 	{
+		cudaGetLastError();
 		delete plan;
 		return MOB200_ERR_CUDA;
 	}
 	uint8_t* base = static_cast<uint8_t*>(plan->arena);
 	plan->T.streams = reinterpret_cast<DevStream*>(base + off_streams);
 	plan->T.block_offset = reinterpret_cast<uint32_t*>(base + off_boff);
-	plan->T.block_stream = reinterpret_cast<uint32_t*>(base + off_bstream);
-	plan->T.chan_offset = reinterpret_cast<uint16_t*>(base + off_chan);
+	plan->T.group_table = reinterpret_cast<uint16_t*>(base + off_table);
+	plan->T.progress = reinterpret_cast<unsigned long long*>(base + off_progress);
 	plan->T.lookback = reinterpret_cast<unsigned long long*>(base + off_look);
+	plan->T.ticket_info = reinterpret_cast<uint2*>(base + off_tinfo);
+	plan->T.block_ticket = reinterpret_cast<uint32_t*>(base + off_bticket);
 	plan->T.status = reinterpret_cast<int32_t*>(base + off_status);
-	plan->T.ticket = reinterpret_cast<uint32_t*>(base + off_ticket);
+	plan->T.counters = reinterpret_cast<uint32_t*>(base + off_counters);
 	plan->T.n_streams = (uint32_t)n;
 	plan->T.total_blocks = (uint32_t)total_blocks;
 	plan->T.epoch = 0;
+	plan->T.walker_lead = ctx->walker_lead;
 
 	// table initialisation is enqueued on the context's stream and waited for, so that a later
 	// mob200_plan_run on any stream sees it (cudaMemset on device memory may return early)
 	bool ok = true;
 	cudaStream_t st = ctx->stream;
-	ok = ok && cudaMemsetAsync(base + off_look, 0, (total_chan / 4) * 8, st) == cudaSuccess; // epoch 0 = never published
-	ok = ok && cudaMemsetAsync(base + off_ticket, 0, 256, st) == cudaSuccess;
+	ok = ok && cudaMemsetAsync(base + off_progress, 0, n * 8, st) == cudaSuccess;             // epoch 0 = never published
+	ok = ok && cudaMemsetAsync(base + off_look, 0, (total_chan / 4) * 8, st) == cudaSuccess;
+	ok = ok && cudaMemsetAsync(base + off_counters, 0, 256, st) == cudaSuccess;
 	if (n)
-		ok = ok && cudaMemcpyAsync(plan->T.streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice, st) == cudaSuccess;
+		ok = ok && cudaMemcpyAsync(base + off_streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice, st) == cudaSuccess;
+	if (total_blocks)
+	{
+		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
+		ok = ok && cudaMemcpyAsync(base + off_bticket, block_ticket.data(), total_blocks * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+	}
 	ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
 	for (int r = 0; r < mob200_Plan::kRing; ++r)
 		for (int i = 0; i < 3; ++i)
@@ -285,9 +347,6 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 		mob200_plan_destroy(plan);
 		return MOB200_ERR_CUDA;
 	}
-
-	uint64_t resident = (uint64_t)ctx->sm_count * ctx->decode_ctas_per_sm;
-	plan->grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(total_blocks, resident));
 	*out = plan;
 	return 0;
 }
@@ -308,9 +367,7 @@ extern "C" void mob200_plan_destroy(mob200_Plan* plan)
 
 extern "C" int mob200_plan_launches(const mob200_Plan* plan)
 {
-	if (!plan || plan->n == 0)
-		return 0;
-	return plan->T.total_blocks ? 2 : 1;
+	return (plan && plan->n) ? 1 : 0; // one fused persistent kernel per run
 }
 
 extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
@@ -326,8 +383,7 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
 	CUDA_TRY(cudaEventRecord(ev[0], st));
-	CUDA_TRY(launch_walk(plan->T, st)); // also resets the ticket counter
-	CUDA_TRY(cudaEventRecord(ev[1], st));
+	CUDA_TRY(cudaEventRecord(ev[1], st)); // (kept for the timing interface: the walk is fused into the decode kernel)
 	CUDA_TRY(launch_decode(plan->T, plan->grid, st));
 	CUDA_TRY(cudaEventRecord(ev[2], st));
 	plan->runs++;

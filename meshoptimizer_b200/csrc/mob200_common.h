@@ -48,36 +48,44 @@ MOB200_HD uint32_t tail_padded(uint32_t vertex_size, uint32_t version)
 	return t < m ? m : t;
 }
 
-// One encoded stream as the kernels see it.  48 bytes.
+// One encoded stream as the kernels see it.  48 bytes.  The host sorts streams by block count
+// (descending) before upload, so that (a) the 32 lanes of a walker warp get streams of similar
+// length and (b) "level b" of the decode order is a prefix of the array.
 struct DevStream
 {
 	const uint8_t* src;    // encoded bytes (device)
 	uint8_t* dst;          // decoded vertices (device)
-	uint64_t src_size;
-	uint64_t chan_base;    // first entry of this stream in the channel-offset table (u16 units);
-	                       // chan_base/4 is its first entry in the look-back table
+	uint64_t chan_base;    // first row of this stream in the group table (one row = one byte-channel
+	                       // of one block); chan_base/4 is its first entry in the look-back table
+	uint32_t src_size;
 	uint32_t vertex_count;
 	uint32_t block_base;   // global id of this stream's block 0
+	uint32_t nblocks;
 	uint16_t vertex_size;
 	uint8_t filter;        // enum mob200_Filter
-	uint8_t version;       // written by the walk kernel
-	int32_t status;        // written by the walk kernel: reference return code
+	uint8_t reserved;
+	uint32_t caller_index; // position of the stream in the caller's array (status is reported there)
 };
 
-// Per-run device tables of a plan.
+// Per-plan device tables.
 struct DevTables
 {
-	DevStream* streams;
-	uint32_t* block_offset; // [total_blocks + n_streams]: stream s, block b at block_base + s + b; entry
-	                        // nblocks = end of the last block.  kInvalidOffset = do not decode.
-	uint32_t* block_stream; // [total_blocks]: owning stream of every global block
-	uint16_t* chan_offset;  // per block, vertex_size entries: byte-channel start relative to the block
-	unsigned long long* lookback; // per block, vertex_size/4 entries: {epoch:30 | state:2} << 32 | value
-	int32_t* status;        // [n_streams]: reference return code per stream (written by the walk kernel)
-	uint32_t* ticket;       // persistent-kernel work counter (reset by the walk kernel)
+	const DevStream* streams;
+	uint32_t* block_offset;       // [total_blocks + n_streams]: stream s, block b at block_base + s + b (entry
+	                              // nblocks = end of the last block); kInvalidOffset = do not decode.  Written
+	                              // by the walker warps, read by the decoders.
+	uint16_t* group_table;        // per (block, byte-channel): 16 entries, one per 16-value group:
+	                              // 0 = all zero, else (offset_in_block << 2) | log2(bits).  Walker -> decoder.
+	unsigned long long* progress; // [n_streams]: epoch << 32 | number of blocks walked (release/acquire)
+	unsigned long long* lookback; // per block, vertex_size/4 entries: (epoch << 2 | state) << 32 | value
+	const uint2* ticket_info;     // [total_blocks]: decode order -> (stream, block)
+	const uint32_t* block_ticket; // [total_blocks]: global block id -> position in the decode order
+	int32_t* status;              // [n_streams] in CALLER order: reference return code per stream
+	uint32_t* counters;           // [0] decode ticket, [1] walker stream ticket, [2] finished roles
 	uint32_t n_streams;
 	uint32_t total_blocks;
-	uint32_t epoch;         // changes every run, so look-back entries never need clearing
+	uint32_t epoch;               // changes every run, so progress / look-back entries never need clearing
+	uint32_t walker_lead;         // walkers stay at most this many tickets ahead of the decode front
 };
 
 } // namespace mob200

@@ -17,14 +17,14 @@
 namespace mob200
 {
 
-constexpr int kWalkThreads = 32;    // one stream per lane; small CTAs spread few streams over many SMs
-constexpr int kDecodeThreads = 128; // one block per CTA iteration: (vertices/16) x (vertex_size/4) <= 128 work items
+constexpr int kDecodeThreads = 128; // warps 0-3 of a CTA decode one block per iteration: (vertices/16) x (vertex_size/4) <= 128 work items
+constexpr int kWalkerThreads = 32;  // warp 4 of a CTA walks 32 streams, one per lane
+constexpr int kCtaThreads = kDecodeThreads + kWalkerThreads;
 
 uint32_t decode_smem_bytes();
 cudaError_t prepare_decode_kernel();
 cudaError_t decode_occupancy(int* ctas_per_sm);
 
-cudaError_t launch_walk(const DevTables& T, cudaStream_t stream);
 cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream);
 cudaError_t launch_filter(int filter, void* data, size_t count, size_t stride, int sm_count, cudaStream_t stream);
 
