@@ -35,7 +35,7 @@ constexpr uint32_t kPlaneBytes = kBlockBytes;
 constexpr uint32_t kSmemStage = 0;
 constexpr uint32_t kSmemPlanes = kSmemStage + kStageBytes;
 constexpr uint32_t kSmemGroupTab = kSmemPlanes + kPlaneBytes;   // u16[vs][16] <= 8 KB only for vs = 256; see below
-constexpr uint32_t kGroupTabBytes = 2048;                       // rows are compacted to `groups` entries: vs*groups*2 <= 1024
+constexpr uint32_t kGroupTabBytes = 1024;                      // rows are compacted to `groups` entries: vs*groups*2 <= 1024
 constexpr uint32_t kSmemTotals = kSmemGroupTab + kGroupTabBytes; // u32[128]: per (chunk, lane) scan totals
 constexpr uint32_t kSmemCarry = kSmemTotals + 128 * 4;          // u32[64]: inclusive prefix of all previous blocks
 constexpr uint32_t kSmemChannels = kSmemCarry + 64 * 4;         // u8[64] channel bytes
@@ -234,8 +234,11 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 			}
 		}
 
-		while (!mbar_try_wait(bar, parity))
+		if (tid == 0)
 		{
+			while (!mbar_try_wait(bar, parity)) // one thread polls; the others sleep in the barrier below
+			{
+			}
 		}
 		parity ^= 1;
 		decoder_sync();
@@ -244,7 +247,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 		const uint32_t total_groups = vs * groups;
 		for (uint32_t gi = tid; gi < total_groups; gi += kDecodeThreads)
 		{
-			uint32_t k = fast_div(gi, P.m_groups, groups);
+			uint32_t k = groups == 16 ? gi >> 4 : fast_div(gi, P.m_groups, groups);
 			uint32_t g = gi - k * groups;
 			uint32_t entry = group_tab[gi];
 			uint32_t o = cb + (entry >> 2);

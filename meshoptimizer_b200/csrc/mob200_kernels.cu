@@ -31,7 +31,7 @@
 namespace mob200
 {
 
-__global__ void __launch_bounds__(kCtaThreads) decode_kernel(DevTables T)
+__global__ void __launch_bounds__(kCtaThreads, 8) decode_kernel(DevTables T)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 
