@@ -99,6 +99,13 @@ struct mob200_Context
 	std::mutex mu;                 // host-pointer entry points share the staging buffers below
 	DeviceBuffer d_in, d_out;
 	PinnedBuffer h_in, h_out;
+	// mob200_decode_batch_host: chunks in flight
+	static const int kHostSlots = 3;
+	cudaStream_t slot_stream[kHostSlots] = {};
+	cudaEvent_t slot_done[kHostSlots] = {};
+	DeviceBuffer slot_arena[kHostSlots];
+	PinnedBuffer slot_h_in[kHostSlots], slot_h_out[kHostSlots];
+	PinnedBuffer h_status;
 };
 
 struct mob200_Plan
@@ -108,6 +115,7 @@ struct mob200_Plan
 	DevTables T = {};
 	int32_t* d_status = nullptr;
 	void* arena = nullptr;
+	bool owns_arena = true;
 	uint32_t grid = 0;
 	// ring of CUDA-event triples (before walk, between, after decode), one per run, recorded on the
 	// launching stream: per-kernel durations can be read back after a timed region without any
@@ -163,6 +171,17 @@ extern "C" void mob200_context_destroy(mob200_Context* ctx)
 	ctx->d_out.release();
 	ctx->h_in.release();
 	ctx->h_out.release();
+	ctx->h_status.release();
+	for (int k = 0; k < mob200_Context::kHostSlots; ++k)
+	{
+		ctx->slot_arena[k].release();
+		ctx->slot_h_in[k].release();
+		ctx->slot_h_out[k].release();
+		if (ctx->slot_stream[k])
+			cudaStreamDestroy(ctx->slot_stream[k]);
+		if (ctx->slot_done[k])
+			cudaEventDestroy(ctx->slot_done[k]);
+	}
 	if (ctx->stream)
 		cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -200,7 +219,9 @@ static size_t align_up(size_t v, size_t a)
 	return (v + a - 1) / a * a;
 }
 
-extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* streams, size_t n, mob200_Plan** out)
+// ext_arena != NULL: the tables live in a caller-owned, grow-only buffer, their initialisation is only
+// ENQUEUED on init_stream (the plan must then run on that stream), and no timing events are created.
+static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, size_t n, DeviceBuffer* ext_arena, cudaStream_t init_stream, bool timing, mob200_Plan** out)
 {
 	if (!ctx || !out || (n && !streams) || n >= 0xffffffffull)
 		return MOB200_ERR_ARGUMENT;
@@ -303,7 +324,17 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	size_t off_counters = align_up(off_status + n * 4, 256);
 	size_t arena_bytes = off_counters + 256;
 
-	if (cudaMalloc(&plan->arena, arena_bytes) != cudaSuccess)
+	if (ext_arena)
+	{
+		if (ext_arena->reserve(arena_bytes))
+		{
+			delete plan;
+			return MOB200_ERR_CUDA;
+		}
+		plan->arena = ext_arena->ptr;
+		plan->owns_arena = false;
+	}
+	else if (cudaMalloc(&plan->arena, arena_bytes) != cudaSuccess)
 	{
 		cudaGetLastError();
 		delete plan;
@@ -327,7 +358,7 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	// table initialisation is enqueued on the context's stream and waited for, so that a later
 	// mob200_plan_run on any stream sees it (cudaMemset on device memory may return early)
 	bool ok = true;
-	cudaStream_t st = ctx->stream;
+	cudaStream_t st = init_stream;
 	ok = ok && cudaMemsetAsync(base + off_progress, 0, n * 8, st) == cudaSuccess;             // epoch 0 = never published
 	ok = ok && cudaMemsetAsync(base + off_look, 0, (total_chan / 4) * 8, st) == cudaSuccess;
 	ok = ok && cudaMemsetAsync(base + off_counters, 0, 256, st) == cudaSuccess;
@@ -338,10 +369,12 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
 		ok = ok && cudaMemcpyAsync(base + off_bticket, block_ticket.data(), total_blocks * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
 	}
-	ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
-	for (int r = 0; r < mob200_Plan::kRing; ++r)
-		for (int i = 0; i < 3; ++i)
-			ok = ok && cudaEventCreate(&plan->ev[r][i]) == cudaSuccess;
+	if (!ext_arena)
+		ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+	if (timing)
+		for (int r = 0; r < mob200_Plan::kRing; ++r)
+			for (int i = 0; i < 3; ++i)
+				ok = ok && cudaEventCreate(&plan->ev[r][i]) == cudaSuccess;
 	if (!ok)
 	{
 		mob200_plan_destroy(plan);
@@ -349,6 +382,13 @@ extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* stre
 	}
 	*out = plan;
 	return 0;
+}
+
+extern "C" int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* streams, size_t n, mob200_Plan** out)
+{
+	if (!ctx)
+		return MOB200_ERR_ARGUMENT;
+	return plan_create_impl(ctx, streams, n, nullptr, ctx->stream, true, out);
 }
 
 extern "C" void mob200_plan_destroy(mob200_Plan* plan)
@@ -360,7 +400,7 @@ extern "C" void mob200_plan_destroy(mob200_Plan* plan)
 		for (int i = 0; i < 3; ++i)
 			if (plan->ev[r][i])
 				cudaEventDestroy(plan->ev[r][i]);
-	if (plan->arena)
+	if (plan->arena && plan->owns_arena)
 		cudaFree(plan->arena);
 	delete plan;
 }
@@ -382,17 +422,22 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 		plan->T.epoch = 1;
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
-	CUDA_TRY(cudaEventRecord(ev[0], st));
-	CUDA_TRY(cudaEventRecord(ev[1], st)); // (kept for the timing interface: the walk is fused into the decode kernel)
+	const bool timed = ev[0] != nullptr;
+	if (timed)
+	{
+		CUDA_TRY(cudaEventRecord(ev[0], st));
+		CUDA_TRY(cudaEventRecord(ev[1], st)); // (kept for the timing interface: the walk is fused into the decode kernel)
+	}
 	CUDA_TRY(launch_decode(plan->T, plan->grid, st));
-	CUDA_TRY(cudaEventRecord(ev[2], st));
+	if (timed)
+		CUDA_TRY(cudaEventRecord(ev[2], st));
 	plan->runs++;
 	return 0;
 }
 
 extern "C" int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms_total, float* ms_walk, float* ms_decode)
 {
-	if (!plan || max_runs < 0)
+	if (!plan || max_runs < 0 || !plan->ev[0][0])
 		return MOB200_ERR_ARGUMENT;
 	if (set_device(plan->ctx))
 		return MOB200_ERR_CUDA;
@@ -465,7 +510,7 @@ extern "C" int mob200_decode_batch_device(mob200_Context* ctx, mob200_Stream* st
 }
 
 // ------------------------------------------------------------------------------------------------
-// host-pointer batch: H2D -> walk + decode -> D2H
+// host-pointer batch: H2D -> walk + decode -> D2H, pipelined in chunks over three CUDA streams
 // ------------------------------------------------------------------------------------------------
 
 static bool is_pinned(const void* p)
@@ -481,6 +526,69 @@ static bool is_pinned(const void* p)
 	return attr.type == cudaMemoryTypeHost;
 }
 
+// A maximal sequence of consecutive streams whose host ranges lie back to back (gaps below 16 bytes, as
+// in a glTF buffer or any packed blob): one cudaMemcpyAsync moves the whole sequence, and the device
+// copy keeps the host layout (including the 16-byte phase of its first byte).
+struct HostRun
+{
+	size_t first, count; // streams [first, first + count)
+	uintptr_t begin;     // host address of the first byte
+	size_t bytes;        // length of the host range
+	size_t dev_base;     // offset of the run in the device arena (256-byte aligned) ...
+	bool pinned;         // ... its first byte sits at dev_base + (begin & 15)
+};
+
+// max_gap: bytes that may lie between two merged ranges.  Inputs tolerate up to 15 (the gap is only read);
+// outputs must be exactly contiguous (a merged device->host copy would overwrite the gap).
+template <typename GetRange>
+static void build_runs(size_t n, GetRange range, size_t max_gap, std::vector<HostRun>& runs, std::vector<size_t>& run_of, size_t& arena_bytes)
+{
+	runs.clear();
+	run_of.assign(n, 0);
+	arena_bytes = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		uintptr_t p;
+		size_t len;
+		range(i, p, len);
+		bool merged = false;
+		if (!runs.empty() && len)
+		{
+			HostRun& r = runs.back();
+			uintptr_t end = r.begin + r.bytes;
+			if (r.bytes && p >= end && p - end <= max_gap)
+			{
+				r.bytes = (size_t)(p + len - r.begin);
+				r.count = i + 1 - r.first;
+				merged = true;
+			}
+		}
+		if (!merged)
+		{
+			HostRun r;
+			r.first = i;
+			r.count = 1;
+			r.begin = p;
+			r.bytes = len;
+			r.dev_base = 0;
+			r.pinned = false;
+			runs.push_back(r);
+		}
+		run_of[i] = runs.size() - 1;
+	}
+	for (HostRun& r : runs)
+	{
+		r.dev_base = arena_bytes;
+		arena_bytes += align_up(r.bytes + 32, 256);
+		r.pinned = r.bytes ? is_pinned(reinterpret_cast<const void*>(r.begin)) : true;
+	}
+}
+
+static size_t run_device_offset(const HostRun& r, uintptr_t p)
+{
+	return r.dev_base + (r.begin & 15) + (size_t)(p - r.begin);
+}
+
 extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* streams, size_t n)
 {
 	if (!ctx || (n && !streams))
@@ -488,10 +596,9 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 	std::lock_guard<std::mutex> lock(ctx->mu);
 	if (set_device(ctx))
 		return MOB200_ERR_CUDA;
+	if (n == 0)
+		return 0;
 
-	// device layout: every stream starts on a 16-byte boundary, input and output each in one arena
-	std::vector<size_t> in_off(n), out_off(n);
-	size_t in_total = 0, out_total = 0;
 	for (size_t i = 0; i < n; ++i)
 	{
 		const mob200_Stream& s = streams[i];
@@ -499,116 +606,178 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 			return MOB200_ERR_ARGUMENT;
 		if (s.vertex_count && !s.dst)
 			return MOB200_ERR_ARGUMENT;
-		in_off[i] = in_total;
-		out_off[i] = out_total;
-		in_total += align_up(s.src ? s.src_size : 0, 16);
-		out_total += align_up(s.vertex_count * s.vertex_size, 16);
 	}
-	if (ctx->d_in.reserve(in_total + 16) || ctx->d_out.reserve(out_total + 16))
-		return MOB200_ERR_CUDA;
 
+	// host ranges -> runs -> device layout
+	std::vector<HostRun> in_runs, out_runs;
+	std::vector<size_t> in_run_of, out_run_of;
+	size_t in_total = 0, out_total = 0;
+	build_runs(n, [&](size_t i, uintptr_t& p, size_t& len) {
+		p = reinterpret_cast<uintptr_t>(streams[i].src);
+		len = streams[i].src ? streams[i].src_size : 0;
+	}, 15, in_runs, in_run_of, in_total);
+	build_runs(n, [&](size_t i, uintptr_t& p, size_t& len) {
+		p = reinterpret_cast<uintptr_t>(streams[i].dst);
+		len = streams[i].vertex_count * streams[i].vertex_size;
+	}, 0, out_runs, out_run_of, out_total);
+	if (ctx->d_in.reserve(in_total + 256) || ctx->d_out.reserve(out_total + 256))
+		return MOB200_ERR_CUDA;
 	uint8_t* d_in = static_cast<uint8_t*>(ctx->d_in.ptr);
 	uint8_t* d_out = static_cast<uint8_t*>(ctx->d_out.ptr);
-	cudaStream_t st = ctx->stream;
-
-	// inputs: pinned caller memory goes straight to the device, pageable memory through pinned staging
-	size_t staged_in = 0;
-	for (size_t i = 0; i < n; ++i)
-		if (streams[i].src && streams[i].src_size && !is_pinned(streams[i].src))
-			staged_in += align_up(streams[i].src_size, 16);
-	if (staged_in && ctx->h_in.reserve(staged_in))
-		return MOB200_ERR_CUDA;
-	{
-		uint8_t* hp = static_cast<uint8_t*>(ctx->h_in.ptr);
-		size_t cursor = 0;
-		for (size_t i = 0; i < n; ++i)
-		{
-			const mob200_Stream& s = streams[i];
-			if (!s.src || !s.src_size)
-				continue;
-			const void* from = s.src;
-			if (!is_pinned(s.src))
-			{
-				memcpy(hp + cursor, s.src, s.src_size);
-				from = hp + cursor;
-				cursor += align_up(s.src_size, 16);
-			}
-			CUDA_TRY(cudaMemcpyAsync(d_in + in_off[i], from, s.src_size, cudaMemcpyHostToDevice, st));
-		}
-	}
 
 	std::vector<mob200_Stream> dev(streams, streams + n);
 	for (size_t i = 0; i < n; ++i)
 	{
-		dev[i].src = streams[i].src ? d_in + in_off[i] : nullptr;
-		dev[i].dst = d_out + out_off[i];
+		dev[i].src = streams[i].src ? d_in + run_device_offset(in_runs[in_run_of[i]], reinterpret_cast<uintptr_t>(streams[i].src)) : nullptr;
+		dev[i].dst = d_out + run_device_offset(out_runs[out_run_of[i]], reinterpret_cast<uintptr_t>(streams[i].dst));
 	}
 
-	mob200_Plan* plan = nullptr;
-	int rc = mob200_plan_create(ctx, dev.data(), n, &plan);
-	if (rc)
-		return rc;
-	rc = mob200_plan_run(plan, st);
-	if (rc)
-	{
-		mob200_plan_destroy(plan);
-		return rc;
-	}
+	// chunks of consecutive streams (~kChunkBytes of traffic each) rotate over kSlots in-flight slots
+	const size_t kChunkBytes = (size_t)96 << 20;
+	const int kSlots = mob200_Context::kHostSlots;
+	for (int k = 0; k < kSlots; ++k)
+		if (!ctx->slot_stream[k])
+		{
+			CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slot_stream[k], cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_done[k], cudaEventDisableTiming));
+		}
 
-	// outputs
-	size_t staged_out = 0;
-	for (size_t i = 0; i < n; ++i)
-		if (streams[i].vertex_count && !is_pinned(streams[i].dst))
-			staged_out += align_up(streams[i].vertex_count * streams[i].vertex_size, 16);
-	if (staged_out && ctx->h_out.reserve(staged_out))
-	{
-		mob200_plan_destroy(plan);
+	std::vector<int> status(n, 0);
+	if (ctx->h_status.reserve(n * sizeof(int)))
 		return MOB200_ERR_CUDA;
-	}
-	{
-		uint8_t* hp = static_cast<uint8_t*>(ctx->h_out.ptr);
-		size_t cursor = 0;
-		for (size_t i = 0; i < n; ++i)
-		{
-			const mob200_Stream& s = streams[i];
-			size_t bytes = s.vertex_count * s.vertex_size;
-			if (!bytes)
-				continue;
-			void* to = s.dst;
-			if (!is_pinned(s.dst))
-			{
-				to = hp + cursor;
-				cursor += align_up(bytes, 16);
-			}
-			cudaError_t e = cudaMemcpyAsync(to, d_out + out_off[i], bytes, cudaMemcpyDeviceToHost, st);
-			if (e != cudaSuccess)
-			{
-				mob200_plan_destroy(plan);
-				return MOB200_ERR_CUDA;
-			}
-		}
-	}
+	int* h_status = static_cast<int*>(ctx->h_status.ptr);
 
-	std::vector<int> status(n);
-	rc = mob200_plan_status(plan, status.data(), st); // synchronises the stream
-	if (rc >= 0)
+	struct SlotWork
 	{
-		uint8_t* hp = static_cast<uint8_t*>(ctx->h_out.ptr);
-		size_t cursor = 0;
-		for (size_t i = 0; i < n; ++i)
+		mob200_Plan* plan = nullptr;
+		size_t i0 = 0, i1 = 0;
+		std::vector<std::pair<void*, std::pair<const void*, size_t>>> unstage; // dst <- (pinned staging, bytes)
+	};
+	SlotWork work[mob200_Context::kHostSlots];
+
+	auto retire = [&](int k) -> int {
+		SlotWork& w = work[k];
+		if (!w.plan)
+			return 0;
+		CUDA_TRY(cudaEventSynchronize(ctx->slot_done[k]));
+		for (auto& u : w.unstage)
+			memcpy(u.first, u.second.first, u.second.second);
+		w.unstage.clear();
+		for (size_t i = w.i0; i < w.i1; ++i)
+			status[i] = h_status[i];
+		mob200_plan_destroy(w.plan);
+		w.plan = nullptr;
+		return 0;
+	};
+
+	size_t chunk_index = 0;
+	for (size_t i0 = 0; i0 < n; ++chunk_index)
+	{
+		size_t i1 = i0, bytes = 0;
+		while (i1 < n && (i1 == i0 || bytes < kChunkBytes))
 		{
-			mob200_Stream& s = streams[i];
-			s.status = status[i];
-			size_t bytes = s.vertex_count * s.vertex_size;
-			if (bytes && !is_pinned(s.dst))
-			{
-				memcpy(s.dst, hp + cursor, bytes);
-				cursor += align_up(bytes, 16);
-			}
+			bytes += (streams[i1].src ? streams[i1].src_size : 0) + streams[i1].vertex_count * streams[i1].vertex_size;
+			++i1;
 		}
+		const int k = (int)(chunk_index % kSlots);
+		if (retire(k))
+			return MOB200_ERR_CUDA;
+		cudaStream_t st = ctx->slot_stream[k];
+		SlotWork& w = work[k];
+		w.i0 = i0;
+		w.i1 = i1;
+
+		// host -> device: one copy per (run, chunk) intersection
+		size_t stage_need_in = 0, stage_need_out = 0;
+		for (size_t i = i0; i < i1;)
+		{
+			const HostRun& r = in_runs[in_run_of[i]];
+			size_t last = std::min(i1, r.first + r.count);
+			if (!r.pinned)
+				for (size_t j = i; j < last; ++j)
+					stage_need_in += align_up(streams[j].src ? streams[j].src_size : 0, 16) + 16;
+			i = last;
+		}
+		for (size_t i = i0; i < i1;)
+		{
+			const HostRun& r = out_runs[out_run_of[i]];
+			size_t last = std::min(i1, r.first + r.count);
+			if (!r.pinned)
+				for (size_t j = i; j < last; ++j)
+					stage_need_out += align_up(streams[j].vertex_count * streams[j].vertex_size, 16) + 16;
+			i = last;
+		}
+		if ((stage_need_in && ctx->slot_h_in[k].reserve(stage_need_in)) || (stage_need_out && ctx->slot_h_out[k].reserve(stage_need_out)))
+			return MOB200_ERR_CUDA;
+
+		size_t cursor = 0;
+		for (size_t i = i0; i < i1;)
+		{
+			const HostRun& r = in_runs[in_run_of[i]];
+			size_t last = std::min(i1, r.first + r.count);
+			// host range of streams [i, last) inside the run
+			uintptr_t h0 = reinterpret_cast<uintptr_t>(streams[i].src);
+			uintptr_t h1 = reinterpret_cast<uintptr_t>(streams[last - 1].src) + (streams[last - 1].src ? streams[last - 1].src_size : 0);
+			if (streams[i].src && h1 > h0)
+			{
+				const void* from = reinterpret_cast<const void*>(h0);
+				if (!r.pinned)
+				{
+					uint8_t* hp = static_cast<uint8_t*>(ctx->slot_h_in[k].ptr) + cursor;
+					memcpy(hp, from, h1 - h0);
+					from = hp;
+					cursor += align_up(h1 - h0, 16) + 16;
+				}
+				CUDA_TRY(cudaMemcpyAsync(d_in + run_device_offset(r, h0), from, h1 - h0, cudaMemcpyHostToDevice, st));
+			}
+			i = last;
+		}
+
+		// decode the chunk
+		int rc = plan_create_impl(ctx, dev.data() + i0, i1 - i0, &ctx->slot_arena[k], st, false, &w.plan);
+		if (rc)
+			return rc;
+		rc = mob200_plan_run(w.plan, st);
+		if (rc)
+			return rc;
+
+		// device -> host
+		cursor = 0;
+		for (size_t i = i0; i < i1;)
+		{
+			const HostRun& r = out_runs[out_run_of[i]];
+			size_t last = std::min(i1, r.first + r.count);
+			uintptr_t h0 = reinterpret_cast<uintptr_t>(streams[i].dst);
+			uintptr_t h1 = reinterpret_cast<uintptr_t>(streams[last - 1].dst) + streams[last - 1].vertex_count * streams[last - 1].vertex_size;
+			if (h1 > h0 && r.bytes)
+			{
+				void* to = reinterpret_cast<void*>(h0);
+				if (!r.pinned)
+				{
+					uint8_t* hp = static_cast<uint8_t*>(ctx->slot_h_out[k].ptr) + cursor;
+					w.unstage.push_back({to, {hp, (size_t)(h1 - h0)}});
+					to = hp;
+					cursor += align_up(h1 - h0, 16) + 16;
+				}
+				CUDA_TRY(cudaMemcpyAsync(to, d_out + run_device_offset(r, h0), h1 - h0, cudaMemcpyDeviceToHost, st));
+			}
+			i = last;
+		}
+		CUDA_TRY(cudaMemcpyAsync(h_status + i0, w.plan->T.status, (i1 - i0) * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(cudaEventRecord(ctx->slot_done[k], st));
+		i0 = i1;
 	}
-	mob200_plan_destroy(plan);
-	return rc;
+	for (int k = 0; k < kSlots; ++k)
+		if (retire(k))
+			return MOB200_ERR_CUDA;
+
+	int failed = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		streams[i].status = status[i];
+		failed += status[i] != 0;
+	}
+	return failed;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -253,3 +253,27 @@ def test_host_api_roundtrip_without_ref(mb, ref_vectors):
     c, vs, _, _ = ref_vectors["codec_meta"][i]
     out = mb.decode_vertex_buffer(int(c), int(vs), ref_vectors[f"codec_{i}_enc"])
     assert np.array_equal(out, ref_vectors[f"codec_{i}_dec"])
+
+
+@needs_ref
+@pytest.mark.parametrize("pinned", [False, True])
+def test_host_batch_chunked_pipeline(mb, pinned):
+    """mob200_decode_batch_host on ~400 MB of traffic: several chunks in flight over the three slots,
+    merged host->device / device->host copies, pageable (staged) and pinned (in place) caller memory"""
+    import torch
+    w = workloads.c2(total=1 << 23, seg=1 << 12, level=2, version=1)
+    out_offs = w.out_offsets()
+    if pinned:
+        h_in = torch.from_numpy(w.blob).pin_memory()
+        h_out = torch.zeros(w.out_bytes() + 64, dtype=torch.uint8).pin_memory()
+        in_ptr, out_ptr, out_np = h_in.data_ptr(), h_out.data_ptr(), h_out.numpy()
+    else:
+        h_out_np = np.zeros(w.out_bytes() + 64, dtype=np.uint8)
+        in_ptr, out_ptr, out_np = w.blob.ctypes.data, h_out_np.ctypes.data, h_out_np
+    items = [(in_ptr + int(w.offsets[i]), int(w.sizes[i]), out_ptr + int(out_offs[i]), int(w.counts[i]), 32, 0) for i in range(w.n)]
+    arr = mb.make_streams(items)
+    rc = mb.lib().mob200_decode_batch_host(mb.default_context().handle, arr, w.n)
+    assert rc == 0
+    assert all(arr[i].status == 0 for i in range(w.n))
+    got = np.concatenate([out_np[int(out_offs[i]) : int(out_offs[i]) + int(w.counts[i]) * 32] for i in range(w.n)])
+    assert np.array_equal(got, w.source), first_mismatch(got, w.source)
