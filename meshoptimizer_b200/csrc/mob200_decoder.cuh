@@ -130,12 +130,14 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 
 				// wait until the walker has published this block
 				const unsigned long long* progress = T.progress + s;
-				for (;;)
+				// (exponential back-off: a starved decoder must not take issue slots from the walker warps)
+				for (uint32_t ns = 64;;)
 				{
 					unsigned long long v = ld_acquire_u64(progress);
 					if ((uint32_t)(v >> 32) == T.epoch && (uint32_t)v > b)
 						break;
-					__nanosleep(128);
+					__nanosleep(ns);
+					ns = ns < 4096 ? ns * 2 : ns;
 				}
 
 				const uint32_t* boff = T.block_offset + d->block_base + s + b;
