@@ -94,7 +94,8 @@ struct mob200_Context
 	int device = 0;
 	int sm_count = 0;
 	int decode_ctas_per_sm = 1;
-	uint32_t walker_lead = 0;      // see DevTables::walker_lead (0 = walkers run unthrottled)
+	uint32_t walker_lead = 0;      // see DevTables::walker_lead
+	int wide_walk_mode = 2;        // 0 / 1 force the walker form, 2 = choose by stream count (MOB200_WIDE_WALK)
 	cudaStream_t stream = nullptr; // used by the host-pointer entry points
 	std::mutex mu;                 // host-pointer entry points share the staging buffers below
 	DeviceBuffer d_in, d_out;
@@ -156,6 +157,8 @@ extern "C" int mob200_context_create(mob200_Context** out, int device)
 	if (ctx->decode_ctas_per_sm < 1)
 		ctx->decode_ctas_per_sm = 1;
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	if (const char* wide = getenv("MOB200_WIDE_WALK"))
+		ctx->wide_walk_mode = atoi(wide);
 	if (const char* lead = getenv("MOB200_WALKER_LEAD"))
 		ctx->walker_lead = (uint32_t)strtoul(lead, nullptr, 10);
 	*out = ctx;
@@ -354,6 +357,8 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.total_blocks = (uint32_t)total_blocks;
 	plan->T.epoch = 0;
 	plan->T.walker_lead = ctx->walker_lead;
+	// few streams: one walker WARP per stream (6x lower latency per block); many: one lane per stream
+	plan->T.wide_walk = ctx->wide_walk_mode == 2 ? (n < (size_t)2 * resident ? 1u : 0u) : (uint32_t)ctx->wide_walk_mode;
 
 	// table initialisation is enqueued on the context's stream and waited for, so that a later
 	// mob200_plan_run on any stream sees it (cudaMemset on device memory may return early)

@@ -85,7 +85,8 @@ struct DevTables
 	uint32_t n_streams;
 	uint32_t total_blocks;
 	uint32_t epoch;               // changes every run, so progress / look-back entries never need clearing
-	uint32_t walker_lead;         // walkers stay at most this many tickets ahead of the decode front
+	uint32_t walker_lead;         // 0xffffffff = walk-only diagnostic mode (decoders off); otherwise unused
+	uint32_t wide_walk;           // 1: one warp per stream (few streams), 0: one lane per stream (many streams)
 };
 
 } // namespace mob200

@@ -27,6 +27,7 @@
 #include "mob200_device.cuh"
 #include "mob200_filters.cuh"
 #include "mob200_walker.cuh"
+#include "mob200_walker_wide.cuh"
 
 namespace mob200
 {
@@ -40,6 +41,8 @@ __global__ void __launch_bounds__(kCtaThreads, 8) decode_kernel(DevTables T)
 		if (T.walker_lead != 0xffffffffu) // 0xffffffff: walk-only diagnostic mode (MOB200_WALKER_LEAD=4294967295)
 			decoder_main(T, smem);
 	}
+	else if (T.wide_walk)
+		walker_main_wide(T, smem + kSmemRing);
 	else
 		walker_main(T, smem + kSmemRing, smem + kSmemRows);
 
