@@ -133,6 +133,12 @@ MESHOPTIMIZER_API int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total
  * this call, so a timed region of repeated mob200_plan_run calls stays asynchronous. */
 MESHOPTIMIZER_API int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms_total, float* ms_walk, float* ms_decode);
 
+/* Diagnostics: cycle counters the kernel accumulates over all CTAs since the last reset -- [0] decoder
+ * warps total, [1..3] of which waiting for staged data / the cross-block carry / the output tile, [4]
+ * producer warps total, [5..7] of which in block metadata / waiting for a free slot / in the look-back.
+ * Synchronises the device.  Returns 0 or MOB200_ERR_*. */
+MESHOPTIMIZER_API int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,7 +56,7 @@ EXPORTS = [
     "mob200_context_create", "mob200_context_destroy", "mob200_plan_create", "mob200_plan_destroy",
     "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
     "mob200_decode_batch_host", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
-    "mob200_plan_last_timing", "mob200_plan_timing_history",
+    "mob200_plan_last_timing", "mob200_plan_timing_history", "mob200_plan_debug_counters",
 ]
 
 
@@ -97,6 +97,8 @@ def lib() -> ctypes.CDLL:
     L.mob200_plan_launches.argtypes = [c_void_p]
     L.mob200_plan_last_timing.restype = c_int
     L.mob200_plan_last_timing.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+    L.mob200_plan_debug_counters.restype = c_int
+    L.mob200_plan_debug_counters.argtypes = [c_void_p, POINTER(ctypes.c_ulonglong), c_int, c_int]
     L.mob200_plan_timing_history.restype = c_int
     L.mob200_plan_timing_history.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
     L.mob200_decode_batch_device.restype = c_int
@@ -283,6 +285,15 @@ class Plan:
         if rc != 0:
             raise RuntimeError(f"mob200_plan_last_timing failed ({rc})")
         return {"total_ms": a.value, "walk_ms": b.value, "decode_ms": c.value}
+
+    def debug_counters(self, reset: bool = True):
+        """cycle counters accumulated by the kernel (see mob200_plan_debug_counters)"""
+        out = (ctypes.c_ulonglong * 8)()
+        rc = lib().mob200_plan_debug_counters(self.handle, out, 8, int(reset))
+        if rc != 0:
+            raise RuntimeError(f"mob200_plan_debug_counters failed ({rc})")
+        names = ["decoder_total", "decoder_wait_full", "decoder_wait_carry", "decoder_wait_tile", "producer_total", "producer_meta", "producer_wait_slot", "producer_lookback"]
+        return dict(zip(names, [int(v) for v in out]))
 
     def timing_history(self, max_runs: int = 64):
         """per-run kernel durations (ms) of the most recent runs, oldest first"""

@@ -422,9 +422,15 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 	if (set_device(plan->ctx))
 		return MOB200_ERR_CUDA;
 	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-	plan->T.epoch = (plan->T.epoch + 1) & 0x3fffffffu;
-	if (plan->T.epoch == 0)
-		plan->T.epoch = 1;
+	if (plan->T.walker_lead != kDecodeOnly || plan->runs == 0) // (decode-only diagnostic: reuse the tables of the first run)
+	{
+		plan->T.epoch = (plan->T.epoch + 1) & 0x3fffffffu;
+		if (plan->T.epoch == 0)
+			plan->T.epoch = 1;
+	}
+	DevTables T = plan->T;
+	if (T.walker_lead == kDecodeOnly && plan->runs == 0)
+		T.walker_lead = 0; // the first run builds the tables
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
 	const bool timed = ev[0] != nullptr;
@@ -433,7 +439,7 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 		CUDA_TRY(cudaEventRecord(ev[0], st));
 		CUDA_TRY(cudaEventRecord(ev[1], st)); // (kept for the timing interface: the walk is fused into the decode kernel)
 	}
-	CUDA_TRY(launch_decode(plan->T, plan->grid, st));
+	CUDA_TRY(launch_decode(T, plan->grid, st));
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ev[2], st));
 	plan->runs++;
@@ -472,6 +478,19 @@ extern "C" int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float
 {
 	int n = mob200_plan_timing_history(plan, 1, ms_total, ms_walk, ms_decode);
 	return n == 1 ? 0 : (n < 0 ? n : MOB200_ERR_ARGUMENT);
+}
+
+extern "C" int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset)
+{
+	if (!plan || !out || count < 0 || count > 8)
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	CUDA_TRY(cudaDeviceSynchronize());
+	CUDA_TRY(cudaMemcpy(out, plan->T.counters + 16, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	if (reset)
+		CUDA_TRY(cudaMemset(plan->T.counters + 16, 0, 8 * sizeof(unsigned long long)));
+	return 0;
 }
 
 extern "C" int mob200_plan_status(mob200_Plan* plan, int* status, void* cuda_stream)

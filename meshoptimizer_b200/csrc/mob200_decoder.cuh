@@ -1,4 +1,25 @@
-// mob200_decoder.cuh -- phases 2+3 of the decode path: the decoder warps (one block per CTA iteration).
+// mob200_decoder.cuh -- phases 2+3 of the decode path: the producer warp and the decoder warps of a CTA.
+//
+// A CTA decodes the blocks  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the level-major decode order
+// (block b of every stream before block b+1 of any: the order in which the walkers publish them).
+//
+//   producer warp   runs ahead of the decoders by up to kSlots blocks.  Per block: ticket -> (stream, block),
+//                   acquire-wait until the walker has published it, allocate a piece of the CTA's staging
+//                   ring, ONE TMA bulk copy for the encoded bytes (16-byte aligned window) and one for the
+//                   block's group-table rows, completion on the slot's `full` mbarrier; then the cross-block
+//                   carry: block 0 starts from the tail's first vertex, later blocks from a decoupled
+//                   look-back over the stream's previous blocks ({flag,value} words published by the
+//                   decoders) -- handed over on the slot's `carry` mbarrier.  Every global-memory latency of
+//                   the block prologue is therefore paid by a warp that has nothing else to do.
+//   decoder warps   thread <-> (4-byte lane q of the vertex, chunk c of 16 vertices); the 16 chunks of a lane
+//                   sit in 16 consecutive threads of one warp.  A thread unpacks its own four 16-value groups
+//                   (byte-channels 4q..4q+3, group c: the work of decodeBytesGroup, reference
+//                   src/vertexcodec.cpp:582-641) straight into registers, transposes them to sixteen 32-bit
+//                   vertex words, undoes zigzag / rotation (decodeDeltas1, :669-699), scans its 16 vertices,
+//                   and the chunk totals are scanned across the 16 threads with warp shuffles -- no shared
+//                   memory and no CTA barrier up to here.  The filter runs on the finished words, the words go
+//                   to a padded vertex tile in shared memory, and after the only CTA barrier of the block the
+//                   tile leaves with 16-byte coalesced stores.
 #pragma once
 
 #include "mob200_device.cuh"
@@ -7,56 +28,59 @@
 namespace mob200
 {
 
-// ------------------------------------------------------------------------------------------------
-// phases 2+3: block decode
-// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSlots = 4;                 // blocks in flight between producer and decoders
+constexpr uint32_t kStageRingBytes = 16384;    // staging ring: encoded bytes + group-table rows of the blocks in flight
+constexpr uint32_t kRowsInRingMaxVs = 64;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
+constexpr uint32_t kRowsInGlobal = 0xffffffffu;
+constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
+constexpr uint32_t kTileBytes = kBlockBytes + 16 * kTilePad;
 
-struct BlockParams
+struct BlockParams // written by the producer, read by the decoders after the slot's `full` barrier (80 bytes)
 {
-	uint32_t ticket;
 	uint32_t valid;
-	uint32_t vs, n, groups, nq;
-	uint32_t version, filter;
-	uint32_t first_block; // block 0 of its stream: the carry is the tail's first vertex
-	uint32_t cb_shift;    // position of the block's first byte inside the staging buffer
-	uint32_t store_align; // 16, 4 or 1
-	uint32_t m_groups;    // ceil(2^32 / groups)          (x / groups    = umulhi(x, m_groups))
-	uint32_t m_nq;        // ceil(2^32 / nq)
-	uint32_t m_chunk;     // ceil(2^32 / (16 * vs))
-	const uint8_t* tail;  // first vertex (vs bytes) then, for v1, vs/4 channel bytes
+	uint32_t vs;
+	uint32_t n;
+	uint32_t groups;      // 16-vertex chunks of the block
+	uint32_t gshift;      // log2 of the chunk count rounded up to a power of two: work item = (q << gshift) | c
+	uint32_t items;       // (vs / 4) << gshift
+	uint32_t stage_off;   // staging-ring offset of the block's first encoded byte
+	uint32_t rows_off;    // staging-ring offset of the block's group-table rows, or kRowsInGlobal
+	uint32_t first;       // block 0 of its stream
+	uint32_t filter;      // enum mob200_Filter
+	uint32_t filter_kind; // 0 none, 1 every 32-bit word on its own (Exp, Oct/Color on 4-byte elements), 2 8-byte elements
+	uint32_t m_chunk;     // ceil(2^32 / (16 * vs)): output byte offset -> chunk
 	uint8_t* out;
-	const uint16_t* rows; // group table rows of this block
-	unsigned long long* lookback; // this block's entries (nq of them); predecessors lie nq entries lower each
+	const uint16_t* rows_global;
+	unsigned long long* lookback; // this block's entries (vs/4 of them); predecessors lie vs/4 entries lower each
+	unsigned long long pad;
 };
 
-// shared-memory map of one CTA (dynamic shared memory, 16-byte aligned pieces)
-constexpr uint32_t kStageBytes = 12672; // >= kMaxEncodedBlock + 15 (alignment) + 16 (over-read slack), also holds the output tile
-constexpr uint32_t kPlaneBytes = kBlockBytes;
+struct SlotData
+{
+	BlockParams P;          // 80 bytes
+	uint32_t pad[4];
+	uint32_t carry[64];     // per 4-byte lane: value of the vertex before the block
+	uint8_t channels[64];   // per 4-byte lane: channel byte (v1) or 0
+};
+
+// shared-memory map of one CTA (dynamic shared memory)
 constexpr uint32_t kSmemStage = 0;
-constexpr uint32_t kSmemPlanes = kSmemStage + kStageBytes;
-constexpr uint32_t kSmemGroupTab = kSmemPlanes + kPlaneBytes;   // u16[vs][16] <= 8 KB only for vs = 256; see below
-constexpr uint32_t kGroupTabBytes = 1024;                      // rows are compacted to `groups` entries: vs*groups*2 <= 1024
-constexpr uint32_t kSmemTotals = kSmemGroupTab + kGroupTabBytes; // u32[128]: per (chunk, lane) scan totals
-constexpr uint32_t kSmemCarry = kSmemTotals + 128 * 4;          // u32[64]: inclusive prefix of all previous blocks
-constexpr uint32_t kSmemChannels = kSmemCarry + 64 * 4;         // u8[64] channel bytes
-constexpr uint32_t kSmemParams = kSmemChannels + 64;            // BlockParams (<= 112 bytes)
-constexpr uint32_t kSmemBarrier = kSmemParams + 112;            // mbarrier
-constexpr uint32_t kSmemRing = (kSmemBarrier + 16 + 127) & ~127u; // walker warp: 32 lanes x 128-byte ring
-constexpr uint32_t kSmemRows = kSmemRing + 32 * 128;               // walker warp: 32 lanes x one 32-byte table row
+constexpr uint32_t kSmemTile = kSmemStage + kStageRingBytes;
+constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;                 // 16 bytes per decoder thread
+constexpr uint32_t kSmemSlots = kSmemPatch + kDecodeThreads * 16;
+constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
+constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;    // producer-private: ring_start[kSlots], ring_len[kSlots]
+constexpr uint32_t kSmemRing = (kSmemProducer + 2 * kSlots * 4 + 127) & ~127u; // walker warp: 32 lanes x 128-byte ring
+constexpr uint32_t kSmemRows = kSmemRing + 32 * 128;                            // walker warp: 32 lanes x one 32-byte table row
 constexpr uint32_t kSmemTotal = kSmemRows + 32 * 32;
 
-static_assert(kStageBytes >= kMaxEncodedBlock + 31, "staging buffer too small");
-static_assert(kStageBytes >= kBlockBytes + 512, "output tile (with per-chunk padding) must fit in the staging buffer");
-static_assert(sizeof(BlockParams) <= 112, "BlockParams grew");
+static_assert(sizeof(BlockParams) == 80 && sizeof(SlotData) == 416, "SlotData layout");
+static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs, "staging ring must hold the largest block");
+static_assert((kTileBytes & 15) == 0 && (kSmemTile & 15) == 0 && (kSmemPatch & 15) == 0 && (kSmemSlots & 15) == 0 && (kSmemBars & 7) == 0, "alignment");
 
 uint32_t decode_smem_bytes()
 {
 	return kSmemTotal;
-}
-
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic, uint32_t d)
-{
-	return d == 1 ? x : __umulhi(x, magic);
 }
 
 __device__ __forceinline__ uint32_t magic_for(uint32_t d)
@@ -71,437 +95,706 @@ __device__ __forceinline__ uint32_t lane_combine(uint32_t a, uint32_t b, uint32_
 	return ((a & ~H) + (b & ~H)) ^ ((a ^ b) & H);
 }
 
-// output tile: row r (vertex) of vs bytes; every 16-row chunk is displaced by `pad` extra bytes
-// (vs rounded up to 16) so that the 4-byte column writes of different chunks fall into different
-// banks while 16-byte reads stay aligned
-__device__ __forceinline__ uint32_t tile_pad(uint32_t vs)
+__device__ __forceinline__ uint32_t lane_mask(uint32_t channel)
 {
-	return (vs + 15u) & ~15u;
+	const uint32_t mode = channel & 3u;
+	return mode == 0 ? 0x80808080u : (mode == 1 ? 0x80008000u : 0xffffffffu);
 }
 
+// output tile: row r (vertex) of vs bytes; every 16-row chunk is displaced by kTilePad bytes so that the
+// 4-byte column writes of the 16 chunks of a lane (16 threads of one warp) fall into different banks
 __device__ __forceinline__ uint32_t tile_offset(uint32_t r, uint32_t vs)
 {
-	return r * vs + (r >> 4) * tile_pad(vs);
+	return r * vs + (r >> 4) * kTilePad;
 }
 
-// byte plane k, group g: 16-byte slots rotated by the channel quad so that the 128-bit reads of the
-// transpose (same group, consecutive quads) hit different banks
-__device__ __forceinline__ uint32_t plane_offset(uint32_t k, uint32_t g, uint32_t groups, uint32_t na)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-	uint32_t slot = g + ((k >> 2) & 15u);
-	slot = groups == 16 ? (slot & 15u) : (slot % groups);
-	return k * na + slot * 16;
+	while (!mbar_try_wait(bar, parity))
+	{
+	}
+}
+
+// same for waits that are expected to be long: the thread may stay suspended for up to `ns` per attempt
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity, uint32_t ns)
+{
+	uint32_t ok;
+	do
+	{
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok)
+		             : "r"(smem_addr(bar)), "r"(parity), "r"(ns)
+		             : "memory");
+	} while (!ok);
+}
+
+// byte-lane helpers (channel mode 0) and 16-bit / xor helpers (modes 1, 2)
+__device__ __forceinline__ uint32_t unzig8x4(uint32_t x)
+{
+	return ((x >> 1) & 0x7f7f7f7fu) ^ ((x & 0x01010101u) * 0xffu);
+}
+
+__device__ __forceinline__ uint32_t add8x4(uint32_t a, uint32_t b)
+{
+	return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+}
+
+// X = 0: two 16-bit lanes (VIADD.16x2), X = ~0: xor
+__device__ __forceinline__ uint32_t combine16(uint32_t a, uint32_t b, uint32_t X)
+{
+	return (__vadd2(a, b) & ~X) | ((a ^ b) & X);
+}
+
+__device__ __forceinline__ uint32_t sum_bytes(const uint4& v)
+{
+	return __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, __dp4a(v.z, 0x01010101u, __dp4a(v.w, 0x01010101u, 0u))));
+}
+
+// ------------------------------------------------------------------------------------------------
+// producer warp
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t kProducerBatch = 8; // blocks whose metadata chains (ticket -> stream -> progress -> offsets) are in flight together, one per lane
+
+// debug counters (cycles, summed over CTAs): see mob200_plan_debug_counters
+enum
+{
+	kDbgDecoderTotal = 0,
+	kDbgDecoderWaitFull,
+	kDbgDecoderWaitCarry,
+	kDbgDecoderWaitTile,
+	kDbgProducerTotal,
+	kDbgProducerMeta,
+	kDbgProducerWaitSlot,
+	kDbgProducerLookback,
+};
+
+__device__ __forceinline__ unsigned long long* debug_counters(const DevTables& T)
+{
+	return reinterpret_cast<unsigned long long*>(T.counters + 16);
+}
+
+__device__ void producer_main(const DevTables& T, uint8_t* smem)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	uint8_t* ring = smem + kSmemStage;
+	SlotData* slots = reinterpret_cast<SlotData*>(smem + kSmemSlots);
+	uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+	uint64_t* carry_bar = full + kSlots;
+	uint64_t* empty = carry_bar + kSlots;
+	uint32_t* ring_start = reinterpret_cast<uint32_t*>(smem + kSmemProducer);
+	uint32_t* ring_len = ring_start + kSlots;
+
+	uint32_t head = 0;  // next free byte of the staging ring
+	uint32_t freed = 0; // blocks [freed, i) of this CTA's sequence are in flight (their ring pieces are live)
+	const uint32_t my_count = blockIdx.x < T.total_blocks ? (T.total_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+	long long dbg_meta = 0, dbg_slot = 0, dbg_look = 0;
+	const long long dbg_t0 = clock64();
+
+	for (uint32_t i0 = 0; i0 < my_count; i0 += kProducerBatch)
+	{
+		// ---- metadata of up to kProducerBatch blocks, one per lane: the dependent global loads of all of them overlap ----
+		const long long c0 = clock64();
+		const uint32_t mi = i0 + lane;
+		const bool has = lane < kProducerBatch && mi < my_count;
+		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0;
+		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
+		if (has)
+		{
+			const uint32_t t = blockIdx.x + mi * gridDim.x;
+			const uint2 info = __ldg(T.ticket_info + t);
+			const uint32_t s = info.x, b = info.y;
+			const DevStream* d = T.streams + s;
+			const uint8_t* src = d->src;
+			const uint32_t vs = d->vertex_size;
+			m_vs = vs;
+			m_b = b;
+			m_filter = d->filter;
+			const uint32_t bv = block_vertices(vs);
+			m_n = min(bv, d->vertex_count - b * bv);
+			m_out = reinterpret_cast<unsigned long long>(d->dst + (uint64_t)b * bv * vs);
+			m_rows = reinterpret_cast<unsigned long long>(T.group_table + (d->chan_base + (uint64_t)b * vs) * 16);
+			m_look = reinterpret_cast<unsigned long long>(T.lookback + (d->chan_base >> 2) + (uint64_t)b * (vs >> 2));
+
+			// wait until the walker has published this block (back-off: a starved producer must not take issue
+			// slots from the walker warps)
+			const unsigned long long* progress = T.progress + s;
+			for (uint32_t ns = 32;;)
+			{
+				unsigned long long v = ld_acquire_u64(progress);
+				if ((uint32_t)(v >> 32) == T.epoch && (uint32_t)v > b)
+					break;
+				__nanosleep(ns);
+				ns = ns < 1024 ? ns * 2 : ns;
+			}
+			const uint32_t* boff = T.block_offset + d->block_base + s + b;
+			const uint32_t off = __ldcg(boff), end = __ldcg(boff + 1);
+			if (off != kInvalidOffset && end != kInvalidOffset)
+			{
+				m_valid = 1;
+				m_version = __ldg(src) & 0x0fu;
+				m_tail = reinterpret_cast<unsigned long long>(src + d->src_size - tail_bytes(vs, m_version));
+				// 16-byte aligned window around [off, end)
+				const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) + off;
+				const uintptr_t a1 = reinterpret_cast<uintptr_t>(src) + end;
+				const uintptr_t lo = a0 & ~uintptr_t(15);
+				const uintptr_t hi = (a1 + 15) & ~uintptr_t(15);
+				m_lo = lo;
+				m_enc = (uint32_t)(hi - lo);
+				m_shift = (uint32_t)(a0 - lo);
+			}
+		}
+		__syncwarp();
+		dbg_meta += clock64() - c0;
+
+		// ---- hand the blocks to the decoders, in order -------------------------------------------------------------
+		const uint32_t in_batch = min(kProducerBatch, my_count - i0);
+		for (uint32_t j = 0; j < in_batch; ++j)
+		{
+			const uint32_t i = i0 + j;
+			const uint32_t slot = i & (kSlots - 1);
+			SlotData& S = slots[slot];
+			const bool valid = __shfl_sync(0xffffffffu, m_valid, j) != 0;
+			const uint32_t vs = __shfl_sync(0xffffffffu, m_vs, j);
+			const uint32_t nq = vs >> 2;
+			const uint32_t version = __shfl_sync(0xffffffffu, m_version, j);
+			const uint32_t b = __shfl_sync(0xffffffffu, m_b, j);
+			const uint8_t* tail = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, m_tail, j));
+
+			// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
+			const long long c1 = clock64();
+			mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 2000);
+			if (i >= kSlots && freed < i - (kSlots - 1))
+				freed = i - (kSlots - 1);
+
+			if (valid)
+			{
+				const uint32_t enc_bytes = __shfl_sync(0xffffffffu, m_enc, j);
+				const uint32_t rows_bytes = vs <= kRowsInRingMaxVs ? 32u * vs : 0u;
+				const uint32_t len = enc_bytes + rows_bytes;
+
+				// allocate `len` contiguous bytes of the ring (pieces are freed in order)
+				uint32_t start;
+				for (;;)
+				{
+					uint32_t f = freed; // oldest live piece
+					while (f < i && ring_len[f & (kSlots - 1)] == 0)
+						++f;
+					if (f == i)
+					{
+						start = 0;
+						break;
+					}
+					const uint32_t so = ring_start[f & (kSlots - 1)];
+					if (head > so)
+					{
+						if (head + len <= kStageRingBytes)
+						{
+							start = head;
+							break;
+						}
+						if (len < so)
+						{
+							start = 0;
+							break;
+						}
+					}
+					else if (head + len < so)
+					{
+						start = head;
+						break;
+					}
+					mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 2000);
+					++freed;
+				}
+				dbg_slot += clock64() - c1;
+				head = start + len;
+				for (uint32_t q = lane; q < nq; q += 32)
+					S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0; // needed by the decoders from the start of the block
+				__syncwarp();
+				if (lane == j)
+				{
+					ring_start[slot] = start;
+					ring_len[slot] = len;
+					BlockParams& P = S.P;
+					const uint32_t groups = (m_n + kGroup - 1) / kGroup;
+					const uint32_t gshift = groups > 8 ? 4u : (groups > 4 ? 3u : (groups > 2 ? 2u : (groups > 1 ? 1u : 0u)));
+					P.valid = 1;
+					P.vs = vs;
+					P.n = m_n;
+					P.groups = groups;
+					P.gshift = gshift;
+					P.items = nq << gshift;
+					P.stage_off = start + m_shift;
+					P.rows_off = rows_bytes ? start + enc_bytes : kRowsInGlobal;
+					P.first = b == 0;
+					P.filter = m_filter;
+					P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs == 4) ? 1u : 2u);
+					P.m_chunk = magic_for(16 * vs);
+					P.out = reinterpret_cast<uint8_t*>(m_out);
+					P.rows_global = reinterpret_cast<const uint16_t*>(m_rows);
+					P.lookback = reinterpret_cast<unsigned long long*>(m_look);
+
+					fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
+					mbar_expect_tx(full + slot, len);
+					tma_load_bulk(ring + start, reinterpret_cast<const void*>(m_lo), enc_bytes, full + slot);
+					if (rows_bytes)
+						tma_load_bulk(ring + start + enc_bytes, P.rows_global, rows_bytes, full + slot);
+				}
+				__syncwarp();
+			}
+			else
+			{
+				dbg_slot += clock64() - c1;
+				__syncwarp();
+				if (lane == j)
+				{
+					ring_len[slot] = 0;
+					S.P.valid = 0;
+					mbar_arrive(full + slot);
+				}
+				__syncwarp();
+			}
+
+			// ---- carry into the block, per 4-byte lane ---------------------------------------------------------------
+			const long long c2 = clock64();
+			if (valid)
+			{
+				const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
+				for (uint32_t q = lane; q < nq; q += 32)
+				{
+					const uint32_t channel = S.channels[q];
+					uint32_t prefix;
+					if (b == 0)
+					{
+						// first vertex stored in the tail (:1846-1849)
+						const uint8_t* fv = tail + q * 4;
+						prefix = (uint32_t)__ldg(fv) | ((uint32_t)__ldg(fv + 1) << 8) | ((uint32_t)__ldg(fv + 2) << 16) | ((uint32_t)__ldg(fv + 3) << 24);
+					}
+					else
+					{
+						// decoupled look-back: add block aggregates (state 1) until an inclusive prefix (state 2)
+						const uint32_t Hq = lane_mask(channel);
+						prefix = 0;
+						const unsigned long long* prev = look + q - nq;
+						for (;;)
+						{
+							const unsigned long long e = ld_volatile_u64(prev);
+							const uint32_t flag = (uint32_t)(e >> 32);
+							if ((flag >> 2) != (T.epoch & 0x3fffffffu) || (flag & 3u) == 0)
+								continue; // not published yet in this run
+							prefix = lane_combine(prefix, (uint32_t)e, Hq);
+							if ((flag & 3u) == 2)
+								break;
+							prev -= nq;
+						}
+					}
+					S.carry[q] = prefix;
+				}
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(carry_bar + slot);
+			dbg_look += clock64() - c2;
+		}
+	}
+
+	if (lane == 0)
+	{
+		unsigned long long* dbg = debug_counters(T);
+		atomicAdd(dbg + kDbgProducerTotal, (unsigned long long)(clock64() - dbg_t0));
+		atomicAdd(dbg + kDbgProducerMeta, (unsigned long long)dbg_meta);
+		atomicAdd(dbg + kDbgProducerWaitSlot, (unsigned long long)dbg_slot);
+		atomicAdd(dbg + kDbgProducerLookback, (unsigned long long)dbg_look);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder warps
+// ------------------------------------------------------------------------------------------------
+
+// one 16-value group -> 16 bytes in registers.  entry = 0: all zero; else (offset << 2) | log2(bits).
+// Groups with all-ones fields take their escape bytes through the thread's 16-byte scratch slot.
+__device__ __forceinline__ uint4 unpack_group(const uint8_t* ring, uint32_t base, uint32_t entry, uint8_t* scratch)
+{
+	uint4 r = make_uint4(0, 0, 0, 0);
+	if (entry == 0)
+		return r;
+	const uint32_t o = base + (entry >> 2);
+	const uint32_t code = entry & 3u;
+	uint32_t m0 = 0, m1 = 0; // all-ones field positions, most significant bit first
+	uint32_t sh = 0, esc = o;
+
+	if (code == 3)
+	{
+		const uint32_t* w = reinterpret_cast<const uint32_t*>(ring) + (o >> 2);
+		const uint32_t s8 = (o & 3u) * 8u;
+		const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+		r.x = __funnelshift_r(a0, a1, s8);
+		r.y = __funnelshift_r(a1, a2, s8);
+		r.z = __funnelshift_r(a2, a3, s8);
+		r.w = __funnelshift_r(a3, a4, s8);
+		return r;
+	}
+	if (code == 2)
+	{
+		const uint32_t* w = reinterpret_cast<const uint32_t*>(ring) + (o >> 2);
+		const uint32_t s8 = (o & 3u) * 8u;
+		const uint32_t a0 = w[0], a1 = w[1], a2 = w[2];
+		const uint32_t x0 = __funnelshift_r(a0, a1, s8), x1 = __funnelshift_r(a1, a2, s8);
+		const uint32_t h0 = (x0 >> 4) & 0x0f0f0f0fu, l0 = x0 & 0x0f0f0f0fu;
+		const uint32_t h1 = (x1 >> 4) & 0x0f0f0f0fu, l1 = x1 & 0x0f0f0f0fu;
+		r.x = __byte_perm(h0, l0, 0x5140);
+		r.y = __byte_perm(h0, l0, 0x7362);
+		r.z = __byte_perm(h1, l1, 0x5140);
+		r.w = __byte_perm(h1, l1, 0x7362);
+		uint32_t t0 = x0 & (x0 >> 1), t1 = x1 & (x1 >> 1);
+		t0 &= t0 >> 2;
+		t1 &= t1 >> 2;
+		// byte-swap: value i of the word ends up at bit 28-4i, so clz enumerates values in order
+		m0 = __byte_perm(t0 & 0x11111111u, 0, 0x0123);
+		m1 = __byte_perm(t1 & 0x11111111u, 0, 0x0123);
+		sh = 2;
+		esc = o + 8;
+	}
+	else if (code == 1)
+	{
+		const uint32_t x = lds_u32_at(ring, o);
+		const uint32_t b0 = x & 0xff, b1 = (x >> 8) & 0xff, b2 = (x >> 16) & 0xff, b3 = x >> 24;
+		r.x = ((b0 * 0x01004010u) & 0x03030300u) | (b0 >> 6);
+		r.y = ((b1 * 0x01004010u) & 0x03030300u) | (b1 >> 6);
+		r.z = ((b2 * 0x01004010u) & 0x03030300u) | (b2 >> 6);
+		r.w = ((b3 * 0x01004010u) & 0x03030300u) | (b3 >> 6);
+		m0 = __byte_perm(x & (x >> 1) & 0x55555555u, 0, 0x0123); // value i at bit 30-2i
+		sh = 1;
+		esc = o + 4;
+	}
+	else
+	{
+		const uint32_t x = lds_u32_at(ring, o) & 0xffffu; // bit i = value i
+		r.x = ((x & 15u) * 0x00204081u) & 0x01010101u;
+		r.y = (((x >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+		r.z = (((x >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+		r.w = ((x >> 12) * 0x00204081u) & 0x01010101u;
+		m0 = __brev(x); // value i at bit 31-i
+		sh = 0;
+		esc = o + 2;
+	}
+
+	if (m0 | m1)
+	{
+		// escape bytes replace the all-ones fields, in order
+		*reinterpret_cast<uint4*>(scratch) = r;
+		uint32_t pos = 0;
+		for (uint32_t m = m0;;)
+		{
+			while (m)
+			{
+				const uint32_t pz = __clz(m);
+				m &= ~(0x80000000u >> pz);
+				scratch[pos + (pz >> sh)] = ring[esc++];
+			}
+			if (pos || m1 == 0)
+				break;
+			pos = 8;
+			m = m1;
+		}
+		r = *reinterpret_cast<const uint4*>(scratch);
+	}
+	return r;
 }
 
 __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 {
-	uint8_t* stage = smem + kSmemStage;
-	uint8_t* planes = smem + kSmemPlanes;
-	uint16_t* group_tab = reinterpret_cast<uint16_t*>(smem + kSmemGroupTab);
-	uint32_t* totals = reinterpret_cast<uint32_t*>(smem + kSmemTotals);
-	uint32_t* carry = reinterpret_cast<uint32_t*>(smem + kSmemCarry);
-	uint8_t* channels = smem + kSmemChannels;
-	BlockParams& P = *reinterpret_cast<BlockParams*>(smem + kSmemParams);
-	uint64_t* bar = reinterpret_cast<uint64_t*>(smem + kSmemBarrier);
+	uint8_t* ring = smem + kSmemStage;
+	uint8_t* tile = smem + kSmemTile;
+	SlotData* slots = reinterpret_cast<SlotData*>(smem + kSmemSlots);
+	uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+	uint64_t* carry_bar = full + kSlots;
+	uint64_t* empty = carry_bar + kSlots;
+	uint64_t* tile_free = empty + kSlots;
 
 	const uint32_t tid = threadIdx.x;
-	uint32_t parity = 0;
+	const uint32_t lane = tid & 31u;
+	const uint32_t warp_base = tid & ~31u;
+	uint8_t* scratch = smem + kSmemPatch + tid * 16;
+	uint32_t tile_uses = 0;
+	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
+	const long long dbg_t0 = clock64();
 
-	if (tid == 0)
+	for (uint32_t i = 0, t = blockIdx.x; t < T.total_blocks; ++i, t += gridDim.x)
 	{
-		mbar_init(bar, 1);
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	decoder_sync();
+		const uint32_t slot = i & (kSlots - 1);
+		const uint32_t phase = (i / kSlots) & 1u;
+		const SlotData& S = slots[slot];
 
-	for (;;)
-	{
-		// ---- take a block ------------------------------------------------------------------------
-		if (tid == 0)
 		{
-			uint32_t ticket = atomicAdd(T.counters, 1u);
-			P.ticket = ticket;
-			P.valid = 0;
-			if (ticket < T.total_blocks)
-			{
-				uint2 info = __ldg(T.ticket_info + ticket);
-				const uint32_t s = info.x, b = info.y;
-				const DevStream* d = T.streams + s;
-
-				// wait until the walker has published this block
-				const unsigned long long* progress = T.progress + s;
-				// (exponential back-off: a starved decoder must not take issue slots from the walker warps)
-				for (uint32_t ns = 64;;)
-				{
-					unsigned long long v = ld_acquire_u64(progress);
-					if ((uint32_t)(v >> 32) == T.epoch && (uint32_t)v > b)
-						break;
-					__nanosleep(ns);
-					ns = ns < 4096 ? ns * 2 : ns;
-				}
-
-				const uint32_t* boff = T.block_offset + d->block_base + s + b;
-				uint32_t off = __ldcg(boff), end = __ldcg(boff + 1);
-				if (off != kInvalidOffset && end != kInvalidOffset)
-				{
-					uint32_t vs = d->vertex_size;
-					uint32_t bv = block_vertices(vs);
-					uint32_t n = min(bv, d->vertex_count - b * bv);
-					uint32_t version = __ldg(d->src) & 0x0fu;
-					uint32_t groups = (n + kGroup - 1) / kGroup;
-					P.valid = 1;
-					P.vs = vs;
-					P.n = n;
-					P.groups = groups;
-					P.nq = vs / 4;
-					P.version = version;
-					P.filter = d->filter;
-					P.first_block = b == 0;
-					P.m_groups = magic_for(groups);
-					P.m_nq = magic_for(vs / 4);
-					P.m_chunk = magic_for(16 * vs);
-					P.tail = d->src + d->src_size - tail_bytes(vs, version);
-					uint8_t* out = d->dst + (uint64_t)b * bv * vs;
-					P.out = out;
-					uintptr_t oa = reinterpret_cast<uintptr_t>(out);
-					P.store_align = (oa & 15) == 0 ? 16 : ((oa & 3) == 0 ? 4 : 1);
-					P.rows = T.group_table + (d->chan_base + (uint64_t)b * vs) * 16;
-					P.lookback = T.lookback + (d->chan_base >> 2) + (uint64_t)b * (vs / 4);
-
-					// stage the encoded block: 16-byte aligned window around [off, end)
-					uintptr_t a0 = reinterpret_cast<uintptr_t>(d->src) + off;
-					uintptr_t a1 = reinterpret_cast<uintptr_t>(d->src) + end;
-					uintptr_t lo = a0 & ~uintptr_t(15);
-					uintptr_t hi = (a1 + 15) & ~uintptr_t(15);
-					P.cb_shift = (uint32_t)(a0 - lo);
-					uint32_t bytes = (uint32_t)(hi - lo);
-					fence_proxy_async(); // earlier generic-proxy accesses of the staging buffer are ordered before the copy
-					mbar_expect_tx(bar, bytes);
-					if (bytes > 0)
-						tma_load_bulk(stage, reinterpret_cast<const void*>(lo), bytes, bar);
-				}
-			}
+			const long long c0 = clock64();
+			mbar_wait(full + slot, phase);
+			dbg_full += clock64() - c0;
 		}
-		decoder_sync();
-
-		if (P.ticket >= T.total_blocks)
-			break;
-		if (!P.valid)
+		if (!S.P.valid)
 		{
-			decoder_sync(); // P is rewritten by thread 0 at the top of the loop
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(empty + slot);
 			continue;
 		}
 
-		const uint32_t vs = P.vs, n = P.n, groups = P.groups, nq = P.nq;
-		const uint32_t na = groups * kGroup;
-		const uint32_t version = P.version;
-		const uint32_t cb = P.cb_shift;
+		const uint4 p0 = *reinterpret_cast<const uint4*>(&S.P.valid);     // valid vs n groups
+		const uint4 p1 = *reinterpret_cast<const uint4*>(&S.P.gshift);    // gshift items stage_off rows_off
+		const uint4 p2 = *reinterpret_cast<const uint4*>(&S.P.first);     // first filter filter_kind m_chunk
+		const uint32_t vs = p0.y, n = p0.z, groups = p0.w;
+		const uint32_t gshift = p1.x, items = p1.y, stage_off = p1.z, rows_off = p1.w;
+		const bool first_block = p2.x != 0;
+		const uint16_t* rows_global = S.P.rows_global;
+		uint8_t* out = S.P.out;
+		unsigned long long* lookback = S.P.lookback;
+		const uint32_t gstride = 1u << gshift;
+		const unsigned long long tag = (unsigned long long)(T.epoch << 2) << 32;
 
-		// group table rows (written by a walker on another SM: read through L2) -> compact rows of
-		// `groups` entries in shared memory, while the bulk copy is in flight
+		// ---- unpack + transpose + deltas + scans, all in registers; one pass per 128 work items ---------------------
+		for (uint32_t base = warp_base; base < items; base += kDecodeThreads)
 		{
-			const uint2* rows = reinterpret_cast<const uint2*>(P.rows);
-			const uint32_t quads = (groups + 3) >> 2; // 4 entries per 8-byte load
-			for (uint32_t i = tid; i < vs * 4; i += kDecodeThreads)
+			const uint32_t item = base + lane;
+			const uint32_t q = item >> gshift;
+			const uint32_t c = item & (gstride - 1u);
+			const bool active = item < items && c < groups;
+
+			uint32_t w[16];
+			uint32_t total = 0;      // lane-wise sum of the 16 deltas
+			uint32_t channel = 0;
+			if (active)
 			{
-				uint32_t k = i >> 2, part = i & 3;
-				if (part < quads)
+				channel = S.channels[q];
+
+				// this thread's four groups: byte-channels 4q..4q+3, group c
+				uint32_t e0, e1, e2, e3;
+				if (rows_off != kRowsInGlobal)
 				{
-					uint2 v = __ldcg(rows + i);
-					uint16_t* dstp = group_tab + k * groups + part * 4;
-					if ((groups & 3u) == 0)
-						*reinterpret_cast<uint2*>(dstp) = v;
-					else
+					const uint16_t* rows = reinterpret_cast<const uint16_t*>(ring + rows_off) + (4 * q) * 16 + c;
+					e0 = rows[0], e1 = rows[16], e2 = rows[32], e3 = rows[48];
+				}
+				else
+				{
+					const uint16_t* rows = rows_global + (4 * q) * 16 + c;
+					e0 = __ldcg(rows), e1 = __ldcg(rows + 16), e2 = __ldcg(rows + 32), e3 = __ldcg(rows + 48);
+				}
+				uint4 pa = unpack_group(ring, stage_off, e0, scratch);
+				uint4 pb = unpack_group(ring, stage_off, e1, scratch);
+				uint4 pc = unpack_group(ring, stage_off, e2, scratch);
+				uint4 pd = unpack_group(ring, stage_off, e3, scratch);
+
+				const bool bytes = (channel & 3u) == 0;
+				if (bytes)
+				{
+					// byte deltas: un-zigzag in plane form, totals with dp4a (one add per four values)
+					pa.x = unzig8x4(pa.x), pa.y = unzig8x4(pa.y), pa.z = unzig8x4(pa.z), pa.w = unzig8x4(pa.w);
+					pb.x = unzig8x4(pb.x), pb.y = unzig8x4(pb.y), pb.z = unzig8x4(pb.z), pb.w = unzig8x4(pb.w);
+					pc.x = unzig8x4(pc.x), pc.y = unzig8x4(pc.y), pc.z = unzig8x4(pc.z), pc.w = unzig8x4(pc.w);
+					pd.x = unzig8x4(pd.x), pd.y = unzig8x4(pd.y), pd.z = unzig8x4(pd.z), pd.w = unzig8x4(pd.w);
+					const uint32_t ta = sum_bytes(pa), tb = sum_bytes(pb), tc = sum_bytes(pc), td = sum_bytes(pd);
+					total = __byte_perm(__byte_perm(ta, tb, 0x0040), __byte_perm(tc, td, 0x0040), 0x5410);
+				}
+
+				// 4 planes x 16 bytes -> 16 vertex words
+				const uint32_t A[4] = {pa.x, pa.y, pa.z, pa.w};
+				const uint32_t B[4] = {pb.x, pb.y, pb.z, pb.w};
+				const uint32_t C[4] = {pc.x, pc.y, pc.z, pc.w};
+				const uint32_t D[4] = {pd.x, pd.y, pd.z, pd.w};
+#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					const uint32_t t0 = __byte_perm(A[j], B[j], 0x5140);
+					const uint32_t t1 = __byte_perm(A[j], B[j], 0x7362);
+					const uint32_t u0 = __byte_perm(C[j], D[j], 0x5140);
+					const uint32_t u1 = __byte_perm(C[j], D[j], 0x7362);
+					w[4 * j + 0] = __byte_perm(t0, u0, 0x5410);
+					w[4 * j + 1] = __byte_perm(t0, u0, 0x7632);
+					w[4 * j + 2] = __byte_perm(t1, u1, 0x5410);
+					w[4 * j + 3] = __byte_perm(t1, u1, 0x7632);
+				}
+
+				if (!bytes)
+				{
+					// 16-bit deltas: un-zigzag per half word; xor: rotate.  r = ((t >> s1) & M) ^ ((t & L) * 0xffff), t = rotl(x, rot)
+					const bool xr = (channel & 3u) == 2;
+					const uint32_t rot = xr ? (32u - (channel >> 4)) & 31u : 0u;
+					const uint32_t s1 = xr ? 0u : 1u;
+					const uint32_t M = xr ? 0xffffffffu : 0x7fff7fffu;
+					const uint32_t L = xr ? 0u : 0x00010001u;
+					const uint32_t X = xr ? 0xffffffffu : 0u;
+#pragma unroll
+					for (int j = 0; j < 16; ++j)
 					{
-						uint32_t left = groups - part * 4;
-						dstp[0] = (uint16_t)v.x;
-						if (left > 1)
-							dstp[1] = (uint16_t)(v.x >> 16);
-						if (left > 2)
-							dstp[2] = (uint16_t)v.y;
-						if (left > 3)
-							dstp[3] = (uint16_t)(v.y >> 16);
+						const uint32_t x = __funnelshift_l(w[j], w[j], rot);
+						w[j] = ((x >> s1) & M) ^ ((x & L) * 0xffffu);
+					}
+					total = w[0];
+#pragma unroll
+					for (int j = 1; j < 16; ++j)
+						total = combine16(total, w[j], X);
+				}
+			}
+			else
+			{
+#pragma unroll
+				for (int j = 0; j < 16; ++j)
+					w[j] = 0;
+			}
+			const uint32_t H = lane_mask(channel);
+
+			// scan of the chunk totals across the gstride threads of this lane q (inactive chunks add 0)
+			uint32_t incl = total;
+			for (uint32_t dlt = 1; dlt < gstride; dlt <<= 1)
+			{
+				const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dlt, gstride);
+				if (c >= dlt)
+					incl = lane_combine(o, incl, H);
+			}
+			uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1, gstride);
+			if (c == 0)
+				excl = 0;
+
+			// (block 0 publishes its inclusive prefix only: a look-back must never step below it)
+			const bool last = active && c == groups - 1;
+			if (last && !first_block)
+				st_volatile_u64(lookback + q, tag | (1ull << 32) | incl); // state 1: aggregate of this block
+
+			if (base == warp_base)
+			{
+				const long long c0 = clock64();
+				mbar_wait(carry_bar + slot, phase);
+				const long long c1 = clock64();
+				mbar_wait(tile_free, (tile_uses & 1u) ^ 1u); // every warp has finished storing the previous tile
+				dbg_carry += c1 - c0;
+				dbg_tile += clock64() - c1;
+			}
+
+			if (active)
+			{
+				const uint32_t carry = S.carry[q];
+				if (last)
+					st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
+				uint32_t v = lane_combine(carry, excl, H);
+				uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
+				if ((channel & 3u) == 0)
+				{
+#pragma unroll
+					for (int j = 0; j < 16; ++j)
+					{
+						v = add8x4(v, w[j]);
+						*reinterpret_cast<uint32_t*>(col) = v;
+						col += vs;
+					}
+				}
+				else
+				{
+					const uint32_t X = (channel & 3u) == 2 ? 0xffffffffu : 0u;
+#pragma unroll
+					for (int j = 0; j < 16; ++j)
+					{
+						v = combine16(v, w[j], X);
+						*reinterpret_cast<uint32_t*>(col) = v;
+						col += vs;
 					}
 				}
 			}
 		}
-		if (tid < nq)
-		{
-			channels[tid] = version ? P.tail[vs + tid] : 0;
-			if (P.first_block)
-			{
-				// carry into block 0 = first vertex stored in the tail (:1846-1849)
-				const uint8_t* fv = P.tail + tid * 4;
-				carry[tid] = (uint32_t)fv[0] | ((uint32_t)fv[1] << 8) | ((uint32_t)fv[2] << 16) | ((uint32_t)fv[3] << 24);
-			}
-		}
+		++tile_uses;
 
-		if (tid == 0)
-		{
-			while (!mbar_try_wait(bar, parity)) // one thread polls; the others sleep in the barrier below
-			{
-			}
-		}
-		parity ^= 1;
-		decoder_sync();
+		// this warp no longer needs the slot (staging bytes, rows, params, carry)
+		__syncwarp();
+		if (lane == 0)
+			mbar_arrive(empty + slot);
 
-		// ---- phase 2: unpack, one thread per 16-value group ------------------------------------------------
-		const uint32_t total_groups = vs * groups;
-		for (uint32_t gi = tid; gi < total_groups; gi += kDecodeThreads)
-		{
-			uint32_t k = groups == 16 ? gi >> 4 : fast_div(gi, P.m_groups, groups);
-			uint32_t g = gi - k * groups;
-			uint32_t entry = group_tab[gi];
-			uint32_t o = cb + (entry >> 2);
-			uint32_t bits = entry ? (1u << (entry & 3u)) : 0u;
-			uint32_t pofs = plane_offset(k, g, groups, na);
-			uint4 r = make_uint4(0, 0, 0, 0);
-			uint32_t m0 = 0, m1 = 0; // sentinel positions, most significant bit first
-			uint32_t sh = 0;
-			uint32_t esc = o;
+		decoder_sync(); // the tile is complete
 
-			if (bits == 8)
-			{
-				const uint32_t* w = reinterpret_cast<const uint32_t*>(stage) + (o >> 2);
-				uint32_t s8 = (o & 3u) * 8u;
-				uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
-				r.x = __funnelshift_r(a0, a1, s8);
-				r.y = __funnelshift_r(a1, a2, s8);
-				r.z = __funnelshift_r(a2, a3, s8);
-				r.w = __funnelshift_r(a3, a4, s8);
-			}
-			else if (bits == 4)
-			{
-				uint32_t x0 = lds_u32_at(stage, o), x1 = lds_u32_at(stage, o + 4);
-				uint32_t h0 = (x0 >> 4) & 0x0f0f0f0fu, l0 = x0 & 0x0f0f0f0fu;
-				uint32_t h1 = (x1 >> 4) & 0x0f0f0f0fu, l1 = x1 & 0x0f0f0f0fu;
-				r.x = __byte_perm(h0, l0, 0x5140);
-				r.y = __byte_perm(h0, l0, 0x7362);
-				r.z = __byte_perm(h1, l1, 0x5140);
-				r.w = __byte_perm(h1, l1, 0x7362);
-				uint32_t t0 = x0 & (x0 >> 1), t1 = x1 & (x1 >> 1);
-				t0 &= t0 >> 2;
-				t1 &= t1 >> 2;
-				// byte-swap: value i of the word ends up at bit 28-4i, so clz enumerates values in order
-				m0 = __byte_perm(t0 & 0x11111111u, 0, 0x0123);
-				m1 = __byte_perm(t1 & 0x11111111u, 0, 0x0123);
-				sh = 2;
-				esc = o + 8;
-			}
-			else if (bits == 2)
-			{
-				uint32_t x = lds_u32_at(stage, o);
-				uint32_t b0 = x & 0xff, b1 = (x >> 8) & 0xff, b2 = (x >> 16) & 0xff, b3 = x >> 24;
-				r.x = ((b0 * 0x01004010u) & 0x03030300u) | (b0 >> 6);
-				r.y = ((b1 * 0x01004010u) & 0x03030300u) | (b1 >> 6);
-				r.z = ((b2 * 0x01004010u) & 0x03030300u) | (b2 >> 6);
-				r.w = ((b3 * 0x01004010u) & 0x03030300u) | (b3 >> 6);
-				m0 = __byte_perm(x & (x >> 1) & 0x55555555u, 0, 0x0123); // value i at bit 30-2i
-				sh = 1;
-				esc = o + 4;
-			}
-			else if (bits == 1)
-			{
-				uint32_t x = lds_u32_at(stage, o) & 0xffffu; // bit i = value i
-				r.x = ((x & 15u) * 0x00204081u) & 0x01010101u;
-				r.y = (((x >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-				r.z = (((x >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-				r.w = ((x >> 12) * 0x00204081u) & 0x01010101u;
-				m0 = __brev(x); // value i at bit 31-i
-				sh = 0;
-				esc = o + 2;
-			}
-
-			*reinterpret_cast<uint4*>(planes + pofs) = r;
-
-			// escape bytes replace the all-ones fields, in order
-			uint32_t base = 0;
-			for (uint32_t m = m0;;)
-			{
-				while (m)
-				{
-					uint32_t pz = __clz(m);
-					m &= ~(0x80000000u >> pz);
-					planes[pofs + base + (pz >> sh)] = stage[esc++];
-				}
-				if (base || m1 == 0)
-					break;
-				base = 8;
-				m = m1;
-			}
-		}
-		decoder_sync();
-
-		// ---- phase 3a: transpose to vertex words, undo zigzag / rotation, scan 16 vertices ---------------------
-		const uint32_t items = groups * nq;
-		uint32_t w[16];
-		uint32_t q = 0, c = 0;
-		uint32_t H = 0x80808080u;
-		const bool active = tid < items;
-		if (active)
-		{
-			c = fast_div(tid, P.m_nq, nq);
-			q = tid - c * nq;
-			uint32_t channel = channels[q];
-			uint32_t mode = channel & 3u;
-			// per-lane constants of the generic transform r = ((t >> s1) & M) ^ ((t & L) * K), t = rotl(x, rot)
-			uint32_t rot = mode == 2 ? (32u - (channel >> 4)) & 31u : 0u;
-			uint32_t s1 = mode == 2 ? 0u : 1u;
-			uint32_t M = mode == 0 ? 0x7f7f7f7fu : (mode == 1 ? 0x7fff7fffu : 0xffffffffu);
-			uint32_t L = mode == 0 ? 0x01010101u : (mode == 1 ? 0x00010001u : 0u);
-			uint32_t K = mode == 0 ? 0xffu : 0xffffu;
-			H = mode == 0 ? 0x80808080u : (mode == 1 ? 0x80008000u : 0xffffffffu);
-
-			uint4 pa = *reinterpret_cast<const uint4*>(planes + plane_offset(4 * q + 0, c, groups, na));
-			uint4 pb = *reinterpret_cast<const uint4*>(planes + plane_offset(4 * q + 1, c, groups, na));
-			uint4 pc = *reinterpret_cast<const uint4*>(planes + plane_offset(4 * q + 2, c, groups, na));
-			uint4 pd = *reinterpret_cast<const uint4*>(planes + plane_offset(4 * q + 3, c, groups, na));
-			const uint32_t A[4] = {pa.x, pa.y, pa.z, pa.w};
-			const uint32_t B[4] = {pb.x, pb.y, pb.z, pb.w};
-			const uint32_t C[4] = {pc.x, pc.y, pc.z, pc.w};
-			const uint32_t D[4] = {pd.x, pd.y, pd.z, pd.w};
-#pragma unroll
-			for (int j = 0; j < 4; ++j)
-			{
-				uint32_t t0 = __byte_perm(A[j], B[j], 0x5140);
-				uint32_t t1 = __byte_perm(A[j], B[j], 0x7362);
-				uint32_t u0 = __byte_perm(C[j], D[j], 0x5140);
-				uint32_t u1 = __byte_perm(C[j], D[j], 0x7362);
-				w[4 * j + 0] = __byte_perm(t0, u0, 0x5410);
-				w[4 * j + 1] = __byte_perm(t0, u0, 0x7632);
-				w[4 * j + 2] = __byte_perm(t1, u1, 0x5410);
-				w[4 * j + 3] = __byte_perm(t1, u1, 0x7632);
-			}
-#pragma unroll
-			for (int i = 0; i < 16; ++i)
-			{
-				uint32_t t = __funnelshift_l(w[i], w[i], rot);
-				w[i] = ((t >> s1) & M) ^ ((t & L) * K);
-			}
-#pragma unroll
-			for (int i = 1; i < 16; ++i)
-				w[i] = lane_combine(w[i - 1], w[i], H);
-			totals[c * nq + q] = w[15];
-		}
-		decoder_sync();
-
-		// ---- phase 3b: per 4-byte lane: in-block exclusive scan of the chunk totals + decoupled look-back ----
-		if (tid < nq)
-		{
-			uint32_t channel = channels[tid];
-			uint32_t mode = channel & 3u;
-			uint32_t Hq = mode == 0 ? 0x80808080u : (mode == 1 ? 0x80008000u : 0xffffffffu);
-			uint32_t run = 0;
-			for (uint32_t cc = 0; cc < groups; ++cc)
-			{
-				uint32_t t = totals[cc * nq + tid];
-				totals[cc * nq + tid] = run;
-				run = lane_combine(run, t, Hq);
-			}
-			// run = aggregate of this block
-			const unsigned long long tag = (unsigned long long)(T.epoch << 2) << 32;
-			unsigned long long* mine = P.lookback + tid;
-			uint32_t prefix;
-			if (P.first_block)
-				prefix = carry[tid];
-			else
-			{
-				st_volatile_u64(mine, tag | (1ull << 32) | run); // state 1: aggregate only
-				prefix = 0;
-				const unsigned long long* prev = mine - nq;
-				for (;;)
-				{
-					unsigned long long e = ld_volatile_u64(prev);
-					uint32_t flag = (uint32_t)(e >> 32);
-					if ((flag >> 2) != (T.epoch & 0x3fffffffu) || (flag & 3u) == 0)
-						continue; // not published yet in this run
-					prefix = lane_combine(prefix, (uint32_t)e, Hq);
-					if ((flag & 3u) == 2)
-						break;
-					prev -= nq;
-				}
-				carry[tid] = prefix;
-			}
-			st_volatile_u64(mine, tag | (2ull << 32) | lane_combine(prefix, run, Hq)); // state 2: inclusive prefix
-		}
-		decoder_sync();
-
-		// ---- phase 3c: add the carry, write the vertex tile (the staging buffer is free now) ----------------------
-		uint8_t* tile = stage;
-		if (active)
-		{
-			uint32_t startv = lane_combine(carry[q], totals[c * nq + q], H);
-			const int filter = (int)P.filter;
-			const bool word_filter = filter == MOB200_FILTER_EXP || ((filter == MOB200_FILTER_OCT || filter == MOB200_FILTER_COLOR) && vs == 4);
-			uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
-#pragma unroll
-			for (int i = 0; i < 16; ++i)
-			{
-				uint32_t v = lane_combine(startv, w[i], H);
-				if (word_filter)
-					v = apply_filter32(v, filter);
-				*reinterpret_cast<uint32_t*>(col + i * vs) = v;
-			}
-		}
-		decoder_sync();
-
-		// ---- phase 3d: 8-byte filters on whole vertices ---------------------------------------------------------------
-		if (P.filter != MOB200_FILTER_NONE && vs == 8 && P.filter != MOB200_FILTER_EXP)
-		{
-			for (uint32_t r = tid; r < n; r += kDecodeThreads)
-			{
-				uint2* e = reinterpret_cast<uint2*>(tile + tile_offset(r, vs));
-				*e = apply_filter64(*e, (int)P.filter);
-			}
-			decoder_sync();
-		}
-
-		// ---- phase 3e: tile -> global memory -----------------------------------------------------------------------------
+		// ---- tile -> global memory, decode filter on the way out ---------------------------------------------------------
 		{
 			const uint32_t nbytes = n * vs;
-			const uint32_t chunk_bytes = 16 * vs;
-			const uint32_t pad = tile_pad(vs);
-			const uint32_t m_chunk = P.m_chunk;
-			uint8_t* out = P.out;
-			if (P.store_align == 16)
+			const uint32_t m_chunk = p2.w;
+			const int filter = (int)p2.y;
+			uint32_t fk = p2.z;
+			const uintptr_t oa = reinterpret_cast<uintptr_t>(out);
+			if (fk != 0 && (oa & 15) != 0)
+			{
+				// unaligned destination: filter inside the tile first (rare)
+				if (fk == 1)
+					for (uint32_t o = tid * 4; o < nbytes; o += kDecodeThreads * 4)
+					{
+						uint32_t* e = reinterpret_cast<uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+						*e = apply_filter32(*e, filter);
+					}
+				else
+					for (uint32_t r = tid; r < n; r += kDecodeThreads)
+					{
+						uint2* e = reinterpret_cast<uint2*>(tile + tile_offset(r, vs));
+						*e = apply_filter64(*e, filter);
+					}
+				decoder_sync();
+				fk = 0;
+			}
+			if ((oa & 15) == 0)
 			{
 				const uint32_t pieces = nbytes >> 4;
 				for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
 				{
-					uint32_t o = j << 4;
-					uint32_t ch = __umulhi(o, m_chunk);
-					uint4 v = *reinterpret_cast<const uint4*>(tile + o + ch * pad);
-					*reinterpret_cast<uint4*>(out + o) = v;
+					const uint32_t o = j << 4;
+					const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+					uint2 lo = p[0], hi = p[1];
+					if (fk == 1)
+					{
+						lo.x = apply_filter32(lo.x, filter), lo.y = apply_filter32(lo.y, filter);
+						hi.x = apply_filter32(hi.x, filter), hi.y = apply_filter32(hi.y, filter);
+					}
+					else if (fk == 2)
+					{
+						lo = apply_filter64(lo, filter);
+						hi = apply_filter64(hi, filter);
+					}
+					*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
 				}
 				const uint32_t rem_words = (nbytes & 15u) >> 2;
 				if (tid < rem_words)
 				{
-					uint32_t o = (pieces << 4) + tid * 4;
-					uint32_t ch = __umulhi(o, m_chunk);
-					*reinterpret_cast<uint32_t*>(out + o) = *reinterpret_cast<const uint32_t*>(tile + o + ch * pad);
+					const uint32_t o = (pieces << 4) + tid * 4;
+					const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+					if (fk == 2)
+					{
+						// one 8-byte element is left over (vs = 8, odd vertex count): thread 0 / 1 keep their half
+						const uint2 r = apply_filter64(*reinterpret_cast<const uint2*>(e - tid), filter);
+						*reinterpret_cast<uint32_t*>(out + o) = tid ? r.y : r.x;
+					}
+					else
+						*reinterpret_cast<uint32_t*>(out + o) = fk == 1 ? apply_filter32(*e, filter) : *e;
 				}
 			}
-			else if (P.store_align == 4)
+			else if ((oa & 3) == 0)
 			{
-				for (uint32_t j = tid; j < (nbytes >> 2); j += kDecodeThreads)
-				{
-					uint32_t o = j << 2;
-					uint32_t ch = __umulhi(o, m_chunk);
-					*reinterpret_cast<uint32_t*>(out + o) = *reinterpret_cast<const uint32_t*>(tile + o + ch * pad);
-				}
+				for (uint32_t o = tid * 4; o < nbytes; o += kDecodeThreads * 4)
+					*reinterpret_cast<uint32_t*>(out + o) = *reinterpret_cast<const uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
 			}
 			else
 			{
 				for (uint32_t o = tid; o < nbytes; o += kDecodeThreads)
-				{
-					uint32_t ch = __umulhi(o, m_chunk);
-					out[o] = tile[o + ch * pad];
-				}
+					out[o] = tile[o + __umulhi(o, m_chunk) * kTilePad];
 			}
 		}
-		decoder_sync(); // the tile / tables are reused by the next block
+		__syncwarp();
+		if (lane == 0)
+			mbar_arrive(tile_free);
+	}
+
+	if (tid == 0)
+	{
+		unsigned long long* dbg = debug_counters(T);
+		atomicAdd(dbg + kDbgDecoderTotal, (unsigned long long)(clock64() - dbg_t0));
+		atomicAdd(dbg + kDbgDecoderWaitFull, (unsigned long long)dbg_full);
+		atomicAdd(dbg + kDbgDecoderWaitCarry, (unsigned long long)dbg_carry);
+		atomicAdd(dbg + kDbgDecoderWaitTile, (unsigned long long)dbg_tile);
 	}
 }
-
 
 } // namespace mob200

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint2 filter_color16(uint2 v)
 }
 
 // element-wise dispatch on 4-byte elements / words (Exp works on every 32-bit word of any stride)
-__device__ __forceinline__ uint32_t apply_filter32(uint32_t v, int filter)
+__device__ __noinline__ uint32_t apply_filter32(uint32_t v, int filter)
 {
 	switch (filter)
 	{
@@ -173,7 +173,7 @@ __device__ __forceinline__ uint32_t apply_filter32(uint32_t v, int filter)
 	}
 }
 
-__device__ __forceinline__ uint2 apply_filter64(uint2 v, int filter)
+__device__ __noinline__ uint2 apply_filter64(uint2 v, int filter)
 {
 	switch (filter)
 	{

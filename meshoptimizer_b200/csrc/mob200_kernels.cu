@@ -7,16 +7,16 @@
 //                  pointer) and publishes, block by block, the byte offset of the block and of each of
 //                  its 16-value groups, plus the reference return code of the stream (:1827-1869).
 //                  Chains of different streams are independent, so 32 of them advance per warp
-//                  instruction; a release store per block hands the block to the decoders.
-//   decoder warps  phases 2+3.  The four decoder warps of a CTA take blocks from a ticket counter in
-//                  level-major order (block b of every stream before block b+1 of any), i.e. in the
-//                  order the walkers produce them.  Per block: one TMA bulk copy stages the encoded
-//                  bytes in shared memory; thread-per-group unpack into byte planes (the work of
-//                  decodeBytesGroup, :582-641); in-register 4x4 byte transposes back to interleaved
-//                  vertices; un-zigzag / rotate and an in-block scan of the deltas (decodeDeltas1,
-//                  :669-699); the cross-block carry (last_vertex, :1592,:1848-1849) is a single-pass
-//                  decoupled look-back per 4-byte lane; the decode filter (src/vertexfilter.cpp) runs
-//                  as an epilogue on the finished tile; 16-byte coalesced stores write the vertices.
+//                  instruction; a release store per block hands the block to the producers.
+//   producer warp  stages the CTA's next blocks (level-major order: block b of every stream before block
+//                  b+1 of any, i.e. the order the walkers produce them): TMA bulk copies of the encoded
+//                  bytes and of the group-table rows into a shared-memory ring, and the cross-block carry
+//                  (last_vertex, :1592,:1848-1849) by a single-pass decoupled look-back per 4-byte lane.
+//   decoder warps  phases 2+3.  Thread-per-(4 byte-channels x 16 vertices): unpack of four 16-value groups
+//                  in registers (decodeBytesGroup, :582-641), 4x4 byte transposes back to interleaved
+//                  vertices, un-zigzag / rotate and scan of the deltas (decodeDeltas1, :669-699) with warp
+//                  shuffles across the block, the decode filter (src/vertexfilter.cpp) as an epilogue on the
+//                  finished words, and 16-byte coalesced stores from a padded tile.
 //
 //   filter_kernel  standalone meshopt_decodeFilter* on a device buffer.
 //
@@ -32,22 +32,51 @@
 namespace mob200
 {
 
-__global__ void __launch_bounds__(kCtaThreads, 8) decode_kernel(DevTables T)
+template <bool kWideWalk>
+__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) decode_kernel(DevTables T)
 {
 	extern __shared__ __align__(128) uint8_t smem[];
 
+	const bool decode_on = T.walker_lead != kWalkOnly;
+	const bool walk_on = T.walker_lead != kDecodeOnly;
+
+	if (decode_on)
+	{
+		if (threadIdx.x == 0)
+		{
+			uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+			for (uint32_t k = 0; k < kSlots; ++k)
+			{
+				mbar_init(bars + k, 1);                          // full: the producer's arrive.expect_tx
+				mbar_init(bars + kSlots + k, 1);                 // carry: the producer
+				mbar_init(bars + 2 * kSlots + k, kDecodeThreads / 32); // empty: one arrival per decoder warp
+			}
+			mbar_init(bars + 3 * kSlots, kDecodeThreads / 32);   // tile_free: one arrival per decoder warp
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+	}
+
 	if (threadIdx.x < kDecodeThreads)
 	{
-		if (T.walker_lead != 0xffffffffu) // 0xffffffff: walk-only diagnostic mode (MOB200_WALKER_LEAD=4294967295)
+		if (decode_on)
 			decoder_main(T, smem);
 	}
-	else if (T.wide_walk)
-		walker_main_wide(T, smem + kSmemRing);
-	else
-		walker_main(T, smem + kSmemRing, smem + kSmemRows);
+	else if (threadIdx.x < kDecodeThreads + kProducerThreads)
+	{
+		if (decode_on)
+			producer_main(T, smem);
+	}
+	else if (walk_on)
+	{
+		if (kWideWalk)
+			walker_main_wide(T, smem + kSmemRing);
+		else
+			walker_main(T, smem + kSmemRing, smem + kSmemRows);
+	}
 
 	// the last role to finish re-arms the counters for the next launch (stream order makes this visible)
-	if ((threadIdx.x & 31u) == 0 && (threadIdx.x == 0 || threadIdx.x == kDecodeThreads))
+	if (threadIdx.x == 0 || threadIdx.x == kDecodeThreads + kProducerThreads)
 	{
 		__threadfence();
 		uint32_t finished = atomicAdd(T.counters + 2, 1u);
@@ -128,19 +157,25 @@ __global__ void __launch_bounds__(256) filter_kernel(uint8_t* data, size_t count
 
 cudaError_t prepare_decode_kernel()
 {
-	return cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+	cudaError_t err = cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+	if (err != cudaSuccess)
+		return err;
+	return cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
 }
 
 cudaError_t decode_occupancy(int* ctas_per_sm)
 {
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, decode_kernel, kCtaThreads, kSmemTotal);
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, decode_kernel<false>, kCtaThreads, kSmemTotal);
 }
 
 cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream)
 {
 	if (T.n_streams == 0)
 		return cudaSuccess;
-	decode_kernel<<<grid, kCtaThreads, kSmemTotal, stream>>>(T);
+	if (T.wide_walk)
+		decode_kernel<true><<<grid, kCtaThreads, kSmemTotal, stream>>>(T);
+	else
+		decode_kernel<false><<<grid, kCtaThreads, kSmemTotal, stream>>>(T);
 	return cudaGetLastError();
 }
 

@@ -17,9 +17,14 @@
 namespace mob200
 {
 
-constexpr int kDecodeThreads = 128; // warps 0-3 of a CTA decode one block per iteration: (vertices/16) x (vertex_size/4) <= 128 work items
-constexpr int kWalkerThreads = 32;  // warp 4 of a CTA walks 32 streams, one per lane
-constexpr int kCtaThreads = kDecodeThreads + kWalkerThreads;
+constexpr int kDecodeThreads = 128;  // warps 0-3 of a CTA decode one block at a time: (vertex_size/4) x (vertices/16, rounded up to a power of two) work items
+constexpr int kProducerThreads = 32; // warp 4 stages the next blocks of the CTA (TMA) and resolves their cross-block carry
+constexpr int kWalkerThreads = 32;   // warp 5 walks 32 streams, one per lane (or one stream with all lanes)
+constexpr int kCtaThreads = kDecodeThreads + kProducerThreads + kWalkerThreads;
+constexpr int kCtasPerSm = 5;        // register budget: 65536 / (5 x 192) -> 64 registers per thread
+
+constexpr uint32_t kWalkOnly = 0xffffffffu;   // DevTables::walker_lead: decoders off (diagnostic)
+constexpr uint32_t kDecodeOnly = 0xfffffffeu; // DevTables::walker_lead: walkers off, tables of the previous run are reused (diagnostic)
 
 uint32_t decode_smem_bytes();
 cudaError_t prepare_decode_kernel();
