@@ -135,7 +135,9 @@ MESHOPTIMIZER_API int mob200_plan_timing_history(mob200_Plan* plan, int max_runs
 
 /* Diagnostics: cycle counters the kernel accumulates over all CTAs since the last reset -- [0] decoder
  * warps total, [1..3] of which waiting for staged data / the cross-block carry / the output tile, [4]
- * producer warps total, [5..7] of which in block metadata / waiting for a free slot / in the look-back.
+ * producer warps total, [5..7] of which in block metadata / waiting for a free slot / in the look-back,
+ * [8] walker warps total, [9..10] of which waiting for ring refills, [11..12] refill points / forced waits.
+ * count <= 16.
  * Synchronises the device.  Returns 0 or MOB200_ERR_*. */
 MESHOPTIMIZER_API int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset);
 

@@ -288,11 +288,12 @@ class Plan:
 
     def debug_counters(self, reset: bool = True):
         """cycle counters accumulated by the kernel (see mob200_plan_debug_counters)"""
-        out = (ctypes.c_ulonglong * 8)()
-        rc = lib().mob200_plan_debug_counters(self.handle, out, 8, int(reset))
+        out = (ctypes.c_ulonglong * 16)()
+        rc = lib().mob200_plan_debug_counters(self.handle, out, 16, int(reset))
         if rc != 0:
             raise RuntimeError(f"mob200_plan_debug_counters failed ({rc})")
-        names = ["decoder_total", "decoder_wait_full", "decoder_wait_carry", "decoder_wait_tile", "producer_total", "producer_meta", "producer_wait_slot", "producer_lookback"]
+        names = ["decoder_total", "decoder_wait_full", "decoder_wait_carry", "decoder_wait_tile", "producer_total", "producer_meta", "producer_wait_slot", "producer_lookback",
+                 "walker_total", "walker_wait_prev", "walker_wait_hard", "walker_refills", "walker_hard_waits", "r13", "r14", "r15"]
         return dict(zip(names, [int(v) for v in out]))
 
     def timing_history(self, max_runs: int = 64):

@@ -482,14 +482,14 @@ extern "C" int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float
 
 extern "C" int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset)
 {
-	if (!plan || !out || count < 0 || count > 8)
+	if (!plan || !out || count < 0 || count > 16)
 		return MOB200_ERR_ARGUMENT;
 	if (set_device(plan->ctx))
 		return MOB200_ERR_CUDA;
 	CUDA_TRY(cudaDeviceSynchronize());
 	CUDA_TRY(cudaMemcpy(out, plan->T.counters + 16, count * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	if (reset)
-		CUDA_TRY(cudaMemset(plan->T.counters + 16, 0, 8 * sizeof(unsigned long long)));
+		CUDA_TRY(cudaMemset(plan->T.counters + 16, 0, 16 * sizeof(unsigned long long)));
 	return 0;
 }
 

@@ -29,8 +29,8 @@ namespace mob200
 {
 
 constexpr uint32_t kSlots = 4;                 // blocks in flight between producer and decoders
-constexpr uint32_t kStageRingBytes = 16384;    // staging ring: encoded bytes + group-table rows of the blocks in flight
-constexpr uint32_t kRowsInRingMaxVs = 64;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
+constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight
+constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
 constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
 constexpr uint32_t kTileBytes = kBlockBytes + 16 * kTilePad;
@@ -70,9 +70,9 @@ constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;                 // 16 by
 constexpr uint32_t kSmemSlots = kSmemPatch + kDecodeThreads * 16;
 constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
 constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;    // producer-private: ring_start[kSlots], ring_len[kSlots]
-constexpr uint32_t kSmemRing = (kSmemProducer + 2 * kSlots * 4 + 127) & ~127u; // walker warp: 32 lanes x 128-byte ring
-constexpr uint32_t kSmemRows = kSmemRing + 32 * 128;                            // walker warp: 32 lanes x one 32-byte table row
-constexpr uint32_t kSmemTotal = kSmemRows + 32 * 32;
+constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
+constexpr uint32_t kSmemWalkerBytes = 32 * 512 + 6 * 4 * 32 + 16;                  // = kWalkSmemBytes (mob200_walker.cuh) >= kWideSmemBytes
+constexpr uint32_t kSmemTotal = kSmemWalker + kSmemWalkerBytes;
 
 static_assert(sizeof(BlockParams) == 80 && sizeof(SlotData) == 416, "SlotData layout");
 static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs, "staging ring must hold the largest block");

@@ -32,10 +32,12 @@
 namespace mob200
 {
 
+static_assert(kSmemWalkerBytes >= kWalkSmemBytes && kSmemWalkerBytes >= kWideSmemBytes, "walker shared-memory region");
+
 template <bool kWideWalk>
 __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) decode_kernel(DevTables T)
 {
-	extern __shared__ __align__(128) uint8_t smem[];
+	extern __shared__ __align__(1024) uint8_t smem[];
 
 	const bool decode_on = T.walker_lead != kWalkOnly;
 	const bool walk_on = T.walker_lead != kDecodeOnly;
@@ -70,9 +72,9 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) decode_kernel(DevTabl
 	else if (walk_on)
 	{
 		if (kWideWalk)
-			walker_main_wide(T, smem + kSmemRing);
+			walker_main_wide(T, smem + kSmemWalker);
 		else
-			walker_main(T, smem + kSmemRing, smem + kSmemRows);
+			walker_main(T, smem + kSmemWalker);
 	}
 
 	// the last role to finish re-arms the counters for the next launch (stream order makes this visible)

@@ -5,16 +5,20 @@
 // 1857-1866 advance a single pointer).  That chain is serial inside a stream but independent across
 // streams, so a walker warp advances 32 streams in lock step, one per lane:
 //
-//   * warp-synchronous, branch-free inner loops with uniform trip counts (a lane that has nothing to
-//     do is predicated off), so that the lanes never diverge: a single diverged lane costs as much as 32;
-//   * each lane streams its encoded bytes through a private 128-byte ring in shared memory fed by
-//     cp.async (32-byte chunks, requested 3-4 chunks ahead of the read position), so the dependent chain
-//     "read packed bits -> count all-ones fields -> next offset" waits for shared memory only;
+//   * warp-synchronous, branch-free group steps, fully unrolled per byte-channel; everything that does not
+//     depend on the running offset (field width, masks, shift amounts, fixed size) comes from a small
+//     shared-memory table indexed by the group's 2-bit selector, so the dependent chain of a step is
+//     "offset -> 3 shared-memory words -> funnel shift -> and/shift -> popc -> add" (~60 cycles);
+//   * each lane streams its encoded bytes through a private 512-byte shared-memory ring of four 128-byte
+//     chunks filled by per-lane TMA bulk copies (cp.async.bulk, completion on warp-shared mbarriers, one
+//     per refill round); the ring is topped up every four groups, so the bytes a step needs were requested
+//     at least one round earlier; after a jump (literal channels are skipped without being read) the
+//     landing chunk is waited for; an L2 prefetch runs a few KB ahead of every lane;
 //   * byte-channels that are zero or literal in every lane (warp vote) are skipped without touching data.
 //
 // Output per block: its byte range (block_offset), one table row of 16 group entries per byte-channel
 // (group_table), a release store of the per-stream progress counter that hands the block to the
-// decoders, and at the end the reference return code of the stream (:1827-1869).
+// producers, and at the end the reference return code of the stream (:1827-1869).
 #pragma once
 
 #include "mob200_device.cuh"
@@ -22,96 +26,165 @@
 namespace mob200
 {
 
-constexpr uint32_t kRingBytes = 128;  // per lane
-constexpr uint32_t kChunkBytes = 32;  // cp.async granule: 2 x 16 bytes
-constexpr uint32_t kRingChunks = kRingBytes / kChunkBytes;
+constexpr uint32_t kWalkRingBytes = 512;  // per lane
+constexpr uint32_t kWalkChunkBytes = 128; // TMA granule
+constexpr uint32_t kWalkChunks = kWalkRingBytes / kWalkChunkBytes;
+constexpr uint32_t kWalkNeed = 208;       // bytes a lane may read between two refill points: header (4) + 8 groups (192) + over-read (12)
+constexpr uint32_t kWalkPrefetch = 4096;  // L2 prefetch distance
+
+// shared-memory layout of the walker warp: 32 rings, the step tables, the refill barrier
+constexpr uint32_t kWalkSmemRings = 0;
+constexpr uint32_t kWalkSmemLut = kWalkSmemRings + 32 * kWalkRingBytes; // 6 selector tables x 4 entries x 32 bytes
+constexpr uint32_t kWalkSmemBars = kWalkSmemLut + 6 * 4 * 32;
+constexpr uint32_t kWalkSmemBytes = kWalkSmemBars + 16;
+
+// step-table entry for one field width (index into {0,1,2,4,8} bits), two 16-byte halves:
+//   a = { mask0, mask1, s1, s2 }: all-ones fields of data word j:  y = x & (x >> s1);  z = y & (y >> s2) & mask_j
+//   b = { fixed bytes, table code, entry mask (0xffff for a group that stores bytes, else 0), 0 }
+__device__ __forceinline__ void walk_lut_entry(uint32_t idx, uint4& a, uint4& b)
+{
+	switch (idx)
+	{
+	case 1: a = make_uint4(0x0000ffffu, 0u, 0u, 0u), b = make_uint4(2u, 0u, 0xffffu, 0u); break;
+	case 2: a = make_uint4(0x55555555u, 0u, 1u, 0u), b = make_uint4(4u, 1u, 0xffffu, 0u); break;
+	case 3: a = make_uint4(0x11111111u, 0x11111111u, 1u, 2u), b = make_uint4(8u, 2u, 0xffffu, 0u); break;
+	case 4: a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(16u, 3u, 0xffffu, 0u); break;
+	default: a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u); break;
+	}
+}
+
+// selector tables: 0 inactive / zero / literal channel (no movement), 1 spare, 2 v0, 3 v1 ctrl 0, 4 v1 ctrl 1, 5 spare
+__device__ __forceinline__ void walk_lut_init(uint8_t* lut, uint32_t lane)
+{
+	if (lane < 24)
+	{
+		const uint32_t table = lane >> 2, sel = lane & 3u;
+		uint32_t idx = 0;
+		switch (table)
+		{
+		case 2: idx = sel ? sel + 1 : 0; break;
+		case 3: idx = sel; break;
+		case 4: idx = sel + 1; break;
+		default: idx = 0; break;
+		}
+		uint4 a, b;
+		walk_lut_entry(idx, a, b);
+		reinterpret_cast<uint4*>(lut)[2 * lane] = a;
+		reinterpret_cast<uint4*>(lut)[2 * lane + 1] = b;
+	}
+	__syncwarp();
+}
 
 // per-lane walker state
 struct WalkLane
 {
-	// stream
 	const uint8_t* src;
-	uint32_t rel0;      // src & 31: all positions below are relative to src rounded down to 32 bytes
+	const uint8_t* org; // src rounded down to 16 bytes: all positions below are relative to it
+	uint32_t rel0;      // src & 15
 	uint32_t rel;       // read position
 	uint32_t rel_end;   // rel0 + size
+	uint32_t limit;     // rel_end rounded up to 16: bytes at or beyond it are never fetched
 	uint32_t vs, count, bv, nblocks, version;
 	int status;
-	// ring
-	uint32_t sbase;     // shared-space address of this lane's ring
-	const uint8_t* org; // src - rel0
-	uint32_t rel_first; // rel0 & ~15: 16-byte pieces before it are outside the readable range
-	uint32_t rel_limit; // 16-byte pieces at or beyond it are never fetched
-	uint32_t next_rel;  // next chunk to request (multiple of kChunkBytes); everything below it has been requested
-	const uint8_t* next_ptr; // org + next_rel
+	uint32_t sbase;     // shared-space address of this lane's ring (512-byte aligned)
+	uint32_t issued;    // chunks [0, issued) have been requested or skipped
+	uint32_t prefetched; // L2 prefetch position (multiple of 128)
 };
 
-// predicated cp.async / commit without branches (a branch would let the lanes of the walker warp diverge)
-__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, bool p)
+// warp-uniform refill state: at most one round of copies is in flight
+struct WalkWarp
 {
-	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}" ::"r"(dst), "l"(src), "r"((uint32_t)p) : "memory");
-}
+	long long dbg_wait, dbg_hard; // cycles spent waiting for the previous round / for a round that is needed at once
+	uint32_t dbg_refills, dbg_hards;
+	uint32_t bar;     // shared-space address of the refill barrier
+	uint32_t phase;   // parity of the barrier phase the next wait is for
+	bool pending;     // a round is in flight
+	uint32_t lut;     // shared-space address of the step tables
+};
 
-__device__ __forceinline__ void cp_async_commit_if(bool p)
+__device__ __forceinline__ void walk_wait(WalkWarp& W)
 {
-	asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q cp.async.commit_group;\n\t}" ::"r"((uint32_t)p) : "memory");
-}
-
-// request the chunk at next_rel (both 16-byte pieces, each only if it lies inside
-// [src & ~15, (src + size + 15) & ~15)) and move next_rel on -- all predicated on p
-template <bool kFirst>
-__device__ __forceinline__ void ring_issue_next(WalkLane& L, bool p)
-{
-	const uint32_t dst = L.sbase + (L.next_rel & (kRingBytes - 1));
-	bool p0 = p && L.next_rel < L.rel_limit;
-	bool p1 = p && L.next_rel + 16 < L.rel_limit;
-	if (kFirst) // only the first chunk of a stream can start before the readable range
+	uint32_t ok;
+	do
 	{
-		p0 = p0 && L.next_rel >= L.rel_first;
-		p1 = p1 && L.next_rel + 16 >= L.rel_first;
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(W.bar), "r"(W.phase) : "memory");
+	} while (!ok);
+	W.phase ^= 1u;
+	W.pending = false;
+}
+
+// Refill point: top up every lane's ring from the chunk that holds L.rel.  The round issued at the previous
+// refill point is waited for first (it was issued half a byte-channel ago and has normally landed), so copies
+// never overtake each other into a ring slot; if a lane is about to read bytes that are only requested now
+// (start of a stream, after a jump over literal channels) this round is waited for, too.
+// `on` lanes take part; the others only keep the warp converged.
+__device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, uint32_t lane)
+{
+	W.dbg_refills++;
+	if (W.pending)
+	{
+		const long long c0 = clock64();
+		walk_wait(W);
+		W.dbg_wait += clock64() - c0;
 	}
-	cp_async16_if(dst, L.next_ptr, p0);
-	cp_async16_if(dst + 16, L.next_ptr + 16, p1);
-	cp_async_commit_if(p);
-	L.next_rel += p ? kChunkBytes : 0u;
-	L.next_ptr += p ? kChunkBytes : 0u;
-}
 
-// Called before every read at L.rel: requests (at most) one more chunk and waits until the chunks that
-// cover [rel, rel + 32 + 11] have landed.  Correct as long as rel advanced by less than one chunk since
-// the previous call (groups advance by <= 24 bytes); larger moves go through ring_jump.  At most two
-// requests are in flight and they are issued in order, so a request never targets a ring slot that an
-// older in-flight request is still writing.
-__device__ __forceinline__ void ring_step(WalkLane& L, bool p)
-{
-	const bool q = p && L.next_rel < (L.rel & ~(kChunkBytes - 1)) + kRingBytes;
-	ring_issue_next<false>(L, q);
-	asm volatile("cp.async.wait_group 2;" ::: "memory");
-}
+	const uint32_t ci = L.rel / kWalkChunkBytes;
+	if (L.issued < ci)
+		L.issued = ci; // chunks that were jumped over are never read
+	const uint32_t landed = L.issued * kWalkChunkBytes;
+	const uint32_t last = (L.limit + kWalkChunkBytes - 1) / kWalkChunkBytes;
+	const uint32_t want = min(ci + kWalkChunks, last);
+	const uint32_t fresh = (on && want > L.issued) ? want - L.issued : 0u; // 0..4 chunks to request
 
-// Reposition the ring after a move of arbitrary size: drain, then request the four chunks at the new position.
-__device__ __forceinline__ void ring_jump(WalkLane& L, bool p)
-{
-	const uint32_t cur = L.rel & ~(kChunkBytes - 1);
-	p = p && L.next_rel < cur + kRingBytes;
-	if (__any_sync(0xffffffffu, p))
+	if (__any_sync(0xffffffffu, fresh != 0))
 	{
-		asm volatile("cp.async.wait_all;" ::: "memory");
-		if (p && L.next_rel < cur)
+		uint32_t bytes = 0;
+		if (fresh)
+			bytes = min((L.issued + fresh) * kWalkChunkBytes, L.limit) - L.issued * kWalkChunkBytes;
+		const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+		fence_proxy_async(); // this lane's earlier (generic-proxy) reads of the ring slots are ordered before the copies that overwrite them
+		if (lane == 0)
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(W.bar), "r"(total) : "memory");
+		__syncwarp();
+#pragma unroll 1
+		for (uint32_t k = 0; k < kWalkChunks; ++k)
 		{
-			L.next_ptr += cur - L.next_rel;
-			L.next_rel = cur;
+			if (k < fresh)
+			{
+				const uint32_t c = L.issued + k;
+				const uint32_t b0 = c * kWalkChunkBytes;
+				const uint32_t sz = min(kWalkChunkBytes, L.limit - b0);
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(L.sbase + (c & (kWalkChunks - 1)) * kWalkChunkBytes),
+				             "l"(L.org + b0), "r"(sz), "r"(W.bar)
+				             : "memory");
+			}
 		}
-#pragma unroll
-		for (uint32_t i = 0; i < kRingChunks; ++i)
-			ring_issue_next<true>(L, p && L.next_rel < cur + kRingBytes);
-		asm volatile("cp.async.wait_group 2;" ::: "memory");
+		L.issued += fresh;
+		W.pending = true;
+		const bool hard = on && min(L.rel + kWalkNeed, L.limit) > landed;
+		if (__any_sync(0xffffffffu, hard))
+		{
+			const long long c0 = clock64();
+			walk_wait(W);
+			W.dbg_hard += clock64() - c0;
+			W.dbg_hards++;
+		}
+	}
+
+	// L2 prefetch a few KB ahead (the decoders' copies and this ring's later refills then hit L2)
+	if (L.prefetched < (L.rel & ~127u))
+		L.prefetched = L.rel & ~127u;
+	if (on && L.prefetched < L.rel + kWalkPrefetch && L.prefetched < L.limit)
+	{
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(L.org + L.prefetched));
+		L.prefetched += 128;
 	}
 }
 
 __device__ __forceinline__ uint32_t ring_word(const WalkLane& L, uint32_t rel)
 {
 	uint32_t v;
-	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(L.sbase + (rel & (kRingBytes - 4))));
+	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(L.sbase | (rel & (kWalkRingBytes - 4))));
 	return v;
 }
 
@@ -120,48 +193,38 @@ __device__ __forceinline__ uint32_t ring_u32_at(const WalkLane& L, uint32_t rel)
 	return __funnelshift_r(ring_word(L, rel), ring_word(L, rel + 4), (rel & 3u) * 8u);
 }
 
-// The 16 group steps of one byte-channel, identical instruction stream for every lane.  selectors holds the
-// 2-bit group selectors (literal lanes: all ones, zero lanes: all zero); `bias` is added to a selector to
-// index the widths {0,1,2,4,8}.  kChecked re-checks the reference's 24-byte rule before each group
-// (:1385,:1415) and is only used close to the end of a stream.  Returns false for a lane that ran out of input.
-template <bool kChecked>
-__device__ __forceinline__ bool walk_groups(WalkLane& L, bool gon0, bool packed, uint32_t selectors, uint32_t bias, uint32_t groups, uint32_t start, uint32_t rowbuf)
+// step-table entry of one group: the two halves of walk_lut_entry
+struct WalkEntry
 {
-	const uint32_t version = L.version;
-	bool bad = false;
-#pragma unroll 4
-	for (uint32_t g = 0; g < 16; ++g, selectors >>= 2)
-	{
-		bool gon = gon0 && g < groups;
-		if (kChecked)
-		{
-			if (gon && packed && L.rel_end - L.rel < kGroupReadLimit)
-				bad = true;
-			gon = gon && !bad;
-		}
-		const uint32_t sel = selectors & 3u;
-		uint32_t idx = sel + (version ? bias : (uint32_t)(sel != 0u)); // index into the widths {0,1,2,4,8}
-		idx = gon ? idx : 0u;
-		const uint32_t entry = idx ? (((L.rel - start) << 2) | (idx - 1u)) : 0u;
-		asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowbuf + g * 2), "r"(entry) : "memory");
-		ring_step(L, idx != 0u);
-		const uint32_t x0 = ring_word(L, L.rel), x1 = ring_word(L, L.rel + 4), x2 = ring_word(L, L.rel + 8);
-		const uint32_t sh = (L.rel & 3u) * 8u;
-		const uint32_t w0 = __funnelshift_r(x0, x1, sh), w1 = __funnelshift_r(x1, x2, sh);
-		// all-ones fields: 1-bit -> the 16 bits themselves, 2-bit -> both bits of a pair, 4-bit -> all four of
-		// a nibble; selected with arithmetic masks (no branches: the lanes must stay converged)
-		const uint32_t a = w0 & (w0 >> 1), c = w1 & (w1 >> 1);
-		const uint32_t f1 = 0u - (uint32_t)(idx == 1u), f2 = 0u - (uint32_t)(idx == 2u), f3 = 0u - (uint32_t)(idx == 3u);
-		const uint32_t m = (w0 & 0xffffu & f1) | (a & 0x55555555u & f2) | (a & (a >> 2) & 0x11111111u & f3);
-		const uint32_t m2 = c & (c >> 2) & 0x11111111u & f3;
-		L.rel += ((1u << idx) & ~1u) + __popc(m) + __popc(m2); // fixed part {0,2,4,8,16} + escape bytes
-	}
-	return !bad;
+	uint4 a, b;
+};
+
+__device__ __forceinline__ WalkEntry walk_entry_load(uint32_t la)
+{
+	WalkEntry e;
+	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.a.x), "=r"(e.a.y), "=r"(e.a.z), "=r"(e.a.w) : "r"(la));
+	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.b.x), "=r"(e.b.y), "=r"(e.b.z), "=r"(e.b.w) : "r"(la + 16u));
+	return e;
+}
+
+// One group step for every lane with the lane's step-table entry for this group (the all-zero entry for a
+// lane that has no such group).  Returns the group-table entry.
+__device__ __forceinline__ uint32_t walk_step(WalkLane& L, const WalkEntry& t, uint32_t start)
+{
+	const uint32_t entry = (((L.rel - start) << 2) + t.b.y) & t.b.z;
+
+	const uint32_t w0 = ring_word(L, L.rel), w1 = ring_word(L, L.rel + 4), w2 = ring_word(L, L.rel + 8);
+	const uint32_t sh = L.rel << 3;
+	const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+	const uint32_t y0 = x0 & (x0 >> t.a.z), y1 = x1 & (x1 >> t.a.z);
+	const uint32_t z0 = y0 & (y0 >> t.a.w) & t.a.x, z1 = y1 & (y1 >> t.a.w) & t.a.y;
+	L.rel += t.b.x + __popc(z0 + 2u * z1); // fixed part {0,2,4,8,16} + escape bytes (the two masks never share a bit after the shift)
+	return entry;
 }
 
 // Walk block `b` of every lane's stream (lanes with on == false only keep the warp converged).
 // Returns false for a lane whose block is malformed.
-__device__ __forceinline__ bool walk_block(WalkLane& L, bool on, uint32_t n, uint16_t* rows, uint32_t rowbuf, uint32_t vs_max)
+__device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, uint32_t n, uint16_t* rows, uint32_t vs_max, uint32_t lane)
 {
 	const uint32_t groups = (n + kGroup - 1) / kGroup;
 	const uint32_t na = groups * kGroup;
@@ -176,7 +239,7 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, bool on, uint32_t n, uin
 
 	// control bytes of the first 64 byte-channels are kept in registers (the ring moves on);
 	// wider vertices read the rest from global memory
-	ring_jump(L, on && !bad);
+	walk_refill(L, W, on && !bad, lane);
 	uint32_t cw0 = ring_u32_at(L, L.rel), cw1 = ring_u32_at(L, L.rel + 4), cw2 = ring_u32_at(L, L.rel + 8), cw3 = ring_u32_at(L, L.rel + 12);
 	const uint8_t* control = L.src + (L.rel - L.rel0);
 	L.rel += (on && !bad) ? ctrl_bytes : 0u;
@@ -206,15 +269,18 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, bool on, uint32_t n, uin
 			if (kon && !bad)
 			{
 				// literal: group g is the 16 raw bytes at rel + 16 g; zero: all entries 0
-				uint32_t e0 = lit ? (((L.rel - start) << 2) | 3u) : 0u;
-				uint32_t step = lit ? (16u << 2) : 0u;
+				const uint32_t e0 = lit ? (((L.rel - start) << 2) | 3u) : 0u;
+				const uint32_t pair = lit ? e0 | ((e0 + (16u << 2)) << 16) : 0u; // entries of groups 0 and 1
+				const uint32_t inc = lit ? (32u << 2) * 0x00010001u : 0u;        // two groups further (no carry between the halves: entries < 2^16)
 				uint32_t w[8];
 #pragma unroll
 				for (uint32_t j = 0; j < 8; ++j)
+					w[j] = pair + inc * j;
+				if (groups < 16)
 				{
-					uint32_t lo = 2 * j < groups ? e0 + step * (2 * j) : 0u;
-					uint32_t hi = 2 * j + 1 < groups ? e0 + step * (2 * j + 1) : 0u;
-					w[j] = lo | (hi << 16);
+#pragma unroll
+					for (uint32_t j = 0; j < 8; ++j)
+						w[j] &= (2 * j < groups ? 0xffffu : 0u) | (2 * j + 1 < groups ? 0xffff0000u : 0u);
 				}
 				row[0] = make_uint4(w[0], w[1], w[2], w[3]);
 				if (groups > 8)
@@ -225,46 +291,70 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, bool on, uint32_t n, uin
 		}
 
 		// general path: at least one lane has a bit-packed channel here; literal and zero lanes run the
-		// same loop as "all groups 8-bit raw" / "all groups zero" without a header
+		// same steps with the all-zero table entry (their position does not move)
 		if (packed && L.rel_end - L.rel < hdr) // (:1376)
 			bad = true;
 		if (lit && L.rel_end - L.rel < na) // (:1546-1554)
 			bad = true;
 		const bool gon0 = kon && !bad;
-		ring_jump(L, gon0); // literal skips of the fast path above may have moved rel arbitrarily
-		uint32_t selectors = packed ? ring_u32_at(L, L.rel) : (lit ? 0xffffffffu : 0u);
-		const uint32_t bias = version ? (lit ? 1u : (packed ? ctrl : 0u)) : 0u;
-		L.rel += (gon0 && packed) ? hdr : 0u;
-		const uint32_t chan_data = L.rel;
+		walk_refill(L, W, gon0, lane); // (literal skips may have moved rel arbitrarily)
+		const bool pk = gon0 && packed;
+		const uint32_t selectors = pk ? ring_u32_at(L, L.rel) : 0u;
+		const uint32_t lutbase = W.lut + (pk ? (version ? 3u + ctrl : 2u) : 0u) * 128u;
+		L.rel += pk ? hdr : 0u;
 
-		// the per-group bounds checks are only needed within reach of the end of the input
-		const bool near_end = gon0 && packed && L.rel_end - L.rel < kGroupReadLimit * groups;
-		bool ok;
-		if (__any_sync(0xffffffffu, near_end))
-			ok = walk_groups<true>(L, gon0, packed, selectors, bias, groups, start, rowbuf);
-		else
-			ok = walk_groups<false>(L, gon0, packed, selectors, bias, groups, start, rowbuf);
-		bad = bad || !ok;
+		// The 16 group steps, branch-free and independent of each other except through L.rel.  The reference
+		// requires 24 readable bytes in front of every group of a bit-packed channel (:1385,:1415); positions only
+		// grow, so the rule holds for all groups iff it holds for the last one (a lane that runs past its input
+		// keeps stepping over stale ring bytes -- memory-safe -- and is rejected below).
+		uint32_t r[8];
+		uint32_t p_last = L.rel;
+		// (the table entry of group g+1 is fetched while group g is stepped: it depends on the selectors only)
+		WalkEntry cur = walk_entry_load(0 < groups ? lutbase + (selectors & 3u) * 32u : W.lut);
+#pragma unroll
+		for (uint32_t g = 0; g < 16; ++g)
+		{
+			if (g == 8)
+				walk_refill(L, W, gon0, lane);
+			WalkEntry nxt = cur;
+			if (g + 1 < 16)
+				nxt = walk_entry_load(g + 1 < groups ? lutbase + ((selectors >> (2 * (g + 1))) & 3u) * 32u : W.lut);
+			p_last = g < groups ? L.rel : p_last;
+			const uint32_t e = walk_step(L, cur, start);
+			if (g & 1u)
+				r[g >> 1] = __byte_perm(r[g >> 1], e, 0x5410);
+			else
+				r[g >> 1] = e;
+			cur = nxt;
+		}
+		if (pk && L.rel_end - min(p_last, L.rel_end) < kGroupReadLimit)
+			bad = true;
 		if (lit && !bad)
-			L.rel = chan_data + n; // a literal channel holds n bytes, not 16 * groups (:1553)
+		{
+			// literal channel: group g is the 16 raw bytes at rel + 16 g; the channel holds n bytes, not 16 * groups (:1553)
+			const uint32_t e0 = ((L.rel - start) << 2) | 3u;
+#pragma unroll
+			for (uint32_t j = 0; j < 8; ++j)
+			{
+				const uint32_t lo = 2 * j < groups ? e0 + (16u << 2) * (2 * j) : 0u;
+				const uint32_t hi = 2 * j + 1 < groups ? e0 + (16u << 2) * (2 * j + 1) : 0u;
+				r[j] = lo | (hi << 16);
+			}
+			L.rel += n;
+		}
 
 		if (kon && !bad)
 		{
-			uint4 lo, hi;
-			asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(rowbuf) : "memory");
-			row[0] = lo;
+			row[0] = make_uint4(r[0], r[1], r[2], r[3]);
 			if (groups > 8)
-			{
-				asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(rowbuf + 16) : "memory");
-				row[1] = hi;
-			}
+				row[1] = make_uint4(r[4], r[5], r[6], r[7]);
 		}
 	}
 	return !bad;
 }
 
 // One pass of the walker warp over 32 streams (lane <-> stream base + lane).
-__device__ void walk_stream_group(const DevTables& T, uint32_t base, uint32_t lane, uint32_t ring_smem, uint32_t rowbuf)
+__device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base, uint32_t lane, uint32_t ring_smem)
 {
 	const uint32_t s = base + lane;
 	const bool have = s < T.n_streams;
@@ -307,19 +397,20 @@ __device__ void walk_stream_group(const DevTables& T, uint32_t base, uint32_t la
 	if (L.status != 0)
 		L.version = 0;
 
-	L.rel0 = (uint32_t)(reinterpret_cast<uintptr_t>(L.src) & (kChunkBytes - 1));
+	L.rel0 = (uint32_t)(reinterpret_cast<uintptr_t>(L.src) & 15u);
+	L.org = L.src - L.rel0;
 	L.rel = L.rel0 + 1;
 	L.rel_end = L.rel0 + size;
+	L.limit = (L.rel_end + 15u) & ~15u;
 	L.sbase = ring_smem;
-	L.org = L.src - L.rel0;
-	L.rel_first = L.rel0 & ~15u;
-	L.rel_limit = (L.rel_end + 15u) & ~15u;
-	L.next_rel = 0;
-	L.next_ptr = L.org;
+	L.issued = 0;
+	L.prefetched = 0;
 
 	const bool framed = have && L.status == 0;
 	uint32_t done = 0; // blocks [0, done) are decodable
 	bool alive = framed;
+	if (!framed)
+		L.limit = 0; // nothing is fetched for a stream that is not walked
 	if (framed && L.nblocks)
 		boff[0] = 1;
 
@@ -330,7 +421,7 @@ __device__ void walk_stream_group(const DevTables& T, uint32_t base, uint32_t la
 		const uint32_t n = on ? min(L.bv, L.count - b * L.bv) : 16u;
 		const uint32_t vs_max = __reduce_max_sync(0xffffffffu, on ? L.vs : 0u);
 		uint16_t* rows = T.group_table + (d->chan_base + (uint64_t)b * L.vs) * 16;
-		const bool ok = walk_block(L, on, n, rows, rowbuf, vs_max);
+		const bool ok = walk_block(L, W, on, n, rows, vs_max, lane);
 		if (on)
 		{
 			if (ok)
@@ -346,7 +437,9 @@ __device__ void walk_stream_group(const DevTables& T, uint32_t base, uint32_t la
 			}
 		}
 	}
-	asm volatile("cp.async.wait_all;" ::: "memory"); // the ring is reused by this lane's next stream
+	// every copy into the rings has landed before the lanes move on to their next streams
+	if (W.pending)
+		walk_wait(W);
 
 	if (have)
 	{
@@ -357,17 +450,32 @@ __device__ void walk_stream_group(const DevTables& T, uint32_t base, uint32_t la
 			// block `done` failed (or the framing did): its end offset and everything after it is invalid
 			for (uint32_t b = framed ? done + 1 : 0; b <= L.nblocks; ++b)
 				boff[b] = kInvalidOffset;
-			st_release_u64(progress, tag | L.nblocks); // nothing more will come: the decoders skip the rest
+			st_release_u64(progress, tag | L.nblocks); // nothing more will come: the producers skip the rest
 		}
 		T.status[d->caller_index] = L.status;
 	}
 }
 
-__device__ void walker_main(const DevTables& T, uint8_t* ring_base, uint8_t* row_base)
+__device__ void walker_main(const DevTables& T, uint8_t* region)
 {
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t ring_smem = smem_addr(ring_base) + lane * kRingBytes;
-	const uint32_t rowbuf = smem_addr(row_base) + lane * 32u;
+	const uint32_t ring_smem = smem_addr(region + kWalkSmemRings) + lane * kWalkRingBytes;
+	if (ring_smem & (kWalkRingBytes - 1))
+		__trap(); // the ring addressing needs 512-byte aligned rings
+	WalkWarp W;
+	W.bar = smem_addr(region + kWalkSmemBars);
+	W.lut = smem_addr(region + kWalkSmemLut);
+	W.phase = 0;
+	W.pending = false;
+	W.dbg_wait = W.dbg_hard = 0;
+	W.dbg_refills = W.dbg_hards = 0;
+	const long long dbg_t0 = clock64();
+	if (lane == 0)
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(W.bar), "r"(1) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	walk_lut_init(region + kWalkSmemLut, lane);
+	__syncwarp();
+
 	for (;;)
 	{
 		uint32_t base = 0;
@@ -376,8 +484,17 @@ __device__ void walker_main(const DevTables& T, uint8_t* ring_base, uint8_t* row
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (base >= T.n_streams)
 			break;
-		walk_stream_group(T, base, lane, ring_smem, rowbuf);
+		walk_stream_group(T, W, base, lane, ring_smem);
 		__syncwarp();
+	}
+	if (lane == 0)
+	{
+		unsigned long long* dbg = reinterpret_cast<unsigned long long*>(T.counters + 16);
+		atomicAdd(dbg + 8, (unsigned long long)(clock64() - dbg_t0));
+		atomicAdd(dbg + 9, (unsigned long long)W.dbg_wait);
+		atomicAdd(dbg + 10, (unsigned long long)W.dbg_hard);
+		atomicAdd(dbg + 11, (unsigned long long)W.dbg_refills);
+		atomicAdd(dbg + 12, (unsigned long long)W.dbg_hards);
 	}
 }
 
