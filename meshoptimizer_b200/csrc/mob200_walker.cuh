@@ -34,7 +34,7 @@ constexpr uint32_t kWalkPrefetch = 4096;  // L2 prefetch distance
 
 // shared-memory layout of the walker warp: 32 rings, the step tables, the refill barrier
 constexpr uint32_t kWalkSmemRings = 0;
-constexpr uint32_t kWalkSmemLut = kWalkSmemRings + 32 * kWalkRingBytes; // 6 selector tables x 4 entries x 32 bytes
+constexpr uint32_t kWalkSmemLut = kWalkSmemRings + 32 * kWalkRingBytes; // 6 selector tables x 4 entries x 32 bytes (128-byte aligned)
 constexpr uint32_t kWalkSmemBars = kWalkSmemLut + 6 * 4 * 32;
 constexpr uint32_t kWalkSmemBytes = kWalkSmemBars + 16;
 
@@ -88,38 +88,37 @@ struct WalkLane
 	int status;
 	uint32_t sbase;     // shared-space address of this lane's ring (512-byte aligned)
 	uint32_t issued;    // chunks [0, issued) have been requested or skipped
+	uint32_t last;      // number of chunks of the stream
+	uint32_t safe_end;  // bytes below it are in the ring (landed) as of the latest refill point
 	uint32_t prefetched; // L2 prefetch position (multiple of 128)
 };
 
 // warp-uniform refill state: at most one round of copies is in flight
 struct WalkWarp
 {
+	long long dbg_steps, dbg_refill; uint32_t dbg_general; // (temporary) cycles in the step loops / in refills, general channels
 	long long dbg_wait, dbg_hard; // cycles spent waiting for the previous round / for a round that is needed at once
 	uint32_t dbg_refills, dbg_hards;
-	uint32_t bar;     // shared-space address of the refill barrier
-	uint32_t phase;   // parity of the barrier phase the next wait is for
 	bool pending;     // a round is in flight
 	uint32_t lut;     // shared-space address of the step tables
 };
 
+// every lane waits for its own copies (cp.async completion is tracked per thread, and a lane only reads its own ring)
 __device__ __forceinline__ void walk_wait(WalkWarp& W)
 {
-	uint32_t ok;
-	do
-	{
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(W.bar), "r"(W.phase) : "memory");
-	} while (!ok);
-	W.phase ^= 1u;
+	asm volatile("cp.async.wait_all;" ::: "memory");
 	W.pending = false;
 }
 
-// Refill point: top up every lane's ring from the chunk that holds L.rel.  The round issued at the previous
-// refill point is waited for first (it was issued half a byte-channel ago and has normally landed), so copies
+// Refill point: top up every lane's ring from the chunk that holds L.rel with 16-byte cp.async copies (all
+// lanes at once: a per-lane TMA bulk copy would be issued lane by lane).  The round issued at the previous
+// refill point is waited for first (it was issued a byte-channel ago and has normally landed), so copies
 // never overtake each other into a ring slot; if a lane is about to read bytes that are only requested now
 // (start of a stream, after a jump over literal channels) this round is waited for, too.
 // `on` lanes take part; the others only keep the warp converged.
 __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, uint32_t lane)
 {
+	const long long dbg_r0 = clock64();
 	W.dbg_refills++;
 	if (W.pending)
 	{
@@ -131,45 +130,49 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 	const uint32_t ci = L.rel / kWalkChunkBytes;
 	if (L.issued < ci)
 		L.issued = ci; // chunks that were jumped over are never read
-	const uint32_t landed = L.issued * kWalkChunkBytes;
-	const uint32_t last = (L.limit + kWalkChunkBytes - 1) / kWalkChunkBytes;
-	const uint32_t want = min(ci + kWalkChunks, last);
-	const uint32_t fresh = (on && want > L.issued) ? want - L.issued : 0u; // 0..4 chunks to request
+	uint32_t safe = L.issued * kWalkChunkBytes; // everything requested so far has landed
+	const uint32_t want = min(ci + kWalkChunks, L.last);
+	const uint32_t fresh = on ? want - min(want, L.issued) : 0u; // 0..4 chunks to request
+	const uint32_t fmax = __reduce_max_sync(0xffffffffu, fresh);
 
-	if (__any_sync(0xffffffffu, fresh != 0))
+	if (fmax)
 	{
-		uint32_t bytes = 0;
-		if (fresh)
-			bytes = min((L.issued + fresh) * kWalkChunkBytes, L.limit) - L.issued * kWalkChunkBytes;
-		const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-		fence_proxy_async(); // this lane's earlier (generic-proxy) reads of the ring slots are ordered before the copies that overwrite them
-		if (lane == 0)
-			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(W.bar), "r"(total) : "memory");
-		__syncwarp();
 #pragma unroll 1
-		for (uint32_t k = 0; k < kWalkChunks; ++k)
+		for (uint32_t k = 0; k < fmax; ++k)
 		{
 			if (k < fresh)
 			{
 				const uint32_t c = L.issued + k;
 				const uint32_t b0 = c * kWalkChunkBytes;
-				const uint32_t sz = min(kWalkChunkBytes, L.limit - b0);
-				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(L.sbase + (c & (kWalkChunks - 1)) * kWalkChunkBytes),
-				             "l"(L.org + b0), "r"(sz), "r"(W.bar)
-				             : "memory");
+				const uint32_t dst = L.sbase + (c & (kWalkChunks - 1)) * kWalkChunkBytes;
+				const uint8_t* src = L.org + b0;
+				if (L.limit - b0 >= kWalkChunkBytes)
+				{
+#pragma unroll
+					for (uint32_t j = 0; j < kWalkChunkBytes; j += 16)
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j), "l"(src + j) : "memory");
+				}
+				else
+				{
+					// last chunk of the stream: only the 16-byte pieces inside [src & ~15, (src + size + 15) & ~15) are read
+					for (uint32_t j = 0; b0 + j < L.limit; j += 16)
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j), "l"(src + j) : "memory");
+				}
 			}
 		}
 		L.issued += fresh;
 		W.pending = true;
-		const bool hard = on && min(L.rel + kWalkNeed, L.limit) > landed;
+		const bool hard = on && min(L.rel + kWalkNeed, L.limit) > safe;
 		if (__any_sync(0xffffffffu, hard))
 		{
 			const long long c0 = clock64();
 			walk_wait(W);
 			W.dbg_hard += clock64() - c0;
 			W.dbg_hards++;
+			safe = L.issued * kWalkChunkBytes;
 		}
 	}
+	L.safe_end = safe;
 
 	// L2 prefetch a few KB ahead (the decoders' copies and this ring's later refills then hit L2)
 	if (L.prefetched < (L.rel & ~127u))
@@ -179,12 +182,20 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 		asm volatile("prefetch.global.L2 [%0];" ::"l"(L.org + L.prefetched));
 		L.prefetched += 128;
 	}
+	W.dbg_refill += clock64() - dbg_r0;
+}
+
+// mid-channel: only when a lane has come within reach of the end of what its ring is known to hold
+__device__ __forceinline__ void walk_refill_if_needed(WalkLane& L, WalkWarp& W, bool on, uint32_t lane)
+{
+	if (__any_sync(0xffffffffu, on && min(L.rel + kWalkNeed, L.limit) > L.safe_end))
+		walk_refill(L, W, on, lane);
 }
 
 __device__ __forceinline__ uint32_t ring_word(const WalkLane& L, uint32_t rel)
 {
 	uint32_t v;
-	asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(L.sbase | (rel & (kWalkRingBytes - 4))));
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(L.sbase | (rel & (kWalkRingBytes - 4))));
 	return v;
 }
 
@@ -202,8 +213,8 @@ struct WalkEntry
 __device__ __forceinline__ WalkEntry walk_entry_load(uint32_t la)
 {
 	WalkEntry e;
-	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.a.x), "=r"(e.a.y), "=r"(e.a.z), "=r"(e.a.w) : "r"(la));
-	asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.b.x), "=r"(e.b.y), "=r"(e.b.z), "=r"(e.b.w) : "r"(la + 16u));
+	asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.a.x), "=r"(e.a.y), "=r"(e.a.z), "=r"(e.a.w) : "r"(la));
+	asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.b.x), "=r"(e.b.y), "=r"(e.b.z), "=r"(e.b.w) : "r"(la + 16u));
 	return e;
 }
 
@@ -233,6 +244,7 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 	const uint32_t version = L.version;
 	const uint32_t ctrl_bytes = version ? L.vs / 4 : 0;
 	bool bad = false;
+	const bool full_blocks = __all_sync(0xffffffffu, !on || groups == 16);
 
 	if (on && L.rel_end - L.rel < ctrl_bytes)
 		bad = true;
@@ -309,24 +321,53 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 		// keeps stepping over stale ring bytes -- memory-safe -- and is rejected below).
 		uint32_t r[8];
 		uint32_t p_last = L.rel;
-		// (the table entry of group g+1 is fetched while group g is stepped: it depends on the selectors only)
-		WalkEntry cur = walk_entry_load(0 < groups ? lutbase + (selectors & 3u) * 32u : W.lut);
-#pragma unroll
-		for (uint32_t g = 0; g < 16; ++g)
+		const long long dbg_s0 = clock64();
+		W.dbg_general++;
+		if (full_blocks)
 		{
-			if (g == 8)
-				walk_refill(L, W, gon0, lane);
-			WalkEntry nxt = cur;
-			if (g + 1 < 16)
-				nxt = walk_entry_load(g + 1 < groups ? lutbase + ((selectors >> (2 * (g + 1))) & 3u) * 32u : W.lut);
-			p_last = g < groups ? L.rel : p_last;
-			const uint32_t e = walk_step(L, cur, start);
-			if (g & 1u)
-				r[g >> 1] = __byte_perm(r[g >> 1], e, 0x5410);
-			else
-				r[g >> 1] = e;
-			cur = nxt;
+			// every lane that is on has 16 groups: fully unrolled, constant shifts.  The shared-memory loads are
+			// volatile and therefore stay in program order: the table entry of group g+1 is requested BEFORE the ring
+			// words of group g, so its latency never sits on the dependent chain of the running offset.
+			WalkEntry t = walk_entry_load(lutbase | ((selectors << 5) & 0x60u));
+#pragma unroll
+			for (uint32_t g = 0; g < 16; ++g)
+			{
+				if (g == 8)
+					walk_refill_if_needed(L, W, gon0, lane);
+				WalkEntry nxt = t;
+				if (g + 1 < 16)
+				{
+					const uint32_t h = g + 1;
+					const uint32_t sel32 = h >= 3 ? (selectors >> (2 * h - 5)) : (selectors << (5 - 2 * h)); // selector * 32
+					nxt = walk_entry_load(lutbase | (sel32 & 0x60u));
+				}
+				if (g == 15)
+					p_last = L.rel;
+				const uint32_t e = walk_step(L, t, start);
+				if (g & 1u)
+					r[g >> 1] = __byte_perm(r[g >> 1], e, 0x5410);
+				else
+					r[g >> 1] = e;
+				t = nxt;
+			}
 		}
+		else
+		{
+			// a partial block (the last one of a stream) somewhere in the warp: rolled loop, entries stored one by one
+#pragma unroll 1
+			for (uint32_t g = 0; g < 16; ++g)
+			{
+				if (g == 8)
+					walk_refill_if_needed(L, W, gon0, lane);
+				const bool has = g < groups;
+				const WalkEntry t = walk_entry_load(has ? lutbase + ((selectors >> (2 * g)) & 3u) * 32u : W.lut);
+				p_last = has ? L.rel : p_last;
+				const uint32_t e = walk_step(L, t, start);
+				if (has && pk)
+					rows[(size_t)k * 16 + g] = (uint16_t)e;
+			}
+		}
+		W.dbg_steps += clock64() - dbg_s0;
 		if (pk && L.rel_end - min(p_last, L.rel_end) < kGroupReadLimit)
 			bad = true;
 		if (lit && !bad)
@@ -343,8 +384,15 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 			L.rel += n;
 		}
 
-		if (kon && !bad)
+		if (kon && !bad && (full_blocks || lit || !pk))
 		{
+			if (!full_blocks && !lit)
+			{
+				// zero channel of a partial block
+#pragma unroll
+				for (uint32_t j = 0; j < 8; ++j)
+					r[j] = 0;
+			}
 			row[0] = make_uint4(r[0], r[1], r[2], r[3]);
 			if (groups > 8)
 				row[1] = make_uint4(r[4], r[5], r[6], r[7]);
@@ -404,6 +452,7 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 	L.limit = (L.rel_end + 15u) & ~15u;
 	L.sbase = ring_smem;
 	L.issued = 0;
+	L.safe_end = 0;
 	L.prefetched = 0;
 
 	const bool framed = have && L.status == 0;
@@ -411,6 +460,7 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 	bool alive = framed;
 	if (!framed)
 		L.limit = 0; // nothing is fetched for a stream that is not walked
+	L.last = (L.limit + kWalkChunkBytes - 1) / kWalkChunkBytes;
 	if (framed && L.nblocks)
 		boff[0] = 1;
 
@@ -463,16 +513,13 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 	if (ring_smem & (kWalkRingBytes - 1))
 		__trap(); // the ring addressing needs 512-byte aligned rings
 	WalkWarp W;
-	W.bar = smem_addr(region + kWalkSmemBars);
 	W.lut = smem_addr(region + kWalkSmemLut);
-	W.phase = 0;
 	W.pending = false;
 	W.dbg_wait = W.dbg_hard = 0;
+	W.dbg_steps = W.dbg_refill = 0;
+	W.dbg_general = 0;
 	W.dbg_refills = W.dbg_hards = 0;
 	const long long dbg_t0 = clock64();
-	if (lane == 0)
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(W.bar), "r"(1) : "memory");
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	walk_lut_init(region + kWalkSmemLut, lane);
 	__syncwarp();
 
@@ -495,6 +542,9 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 		atomicAdd(dbg + 10, (unsigned long long)W.dbg_hard);
 		atomicAdd(dbg + 11, (unsigned long long)W.dbg_refills);
 		atomicAdd(dbg + 12, (unsigned long long)W.dbg_hards);
+		atomicAdd(dbg + 13, (unsigned long long)W.dbg_steps);
+		atomicAdd(dbg + 14, (unsigned long long)W.dbg_refill);
+		atomicAdd(dbg + 15, (unsigned long long)W.dbg_general);
 	}
 }
 

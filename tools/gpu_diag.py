@@ -51,5 +51,6 @@ print("  decoders: wait full %.1f%% carry %.1f%% tile %.1f%% | producers: meta %
     100 * dbg["producer_meta"] / pt, 100 * dbg["producer_wait_slot"] / pt, 100 * dbg["producer_lookback"] / pt, dt / runs / max(1, plan.grid if hasattr(plan, "grid") else 740)))
 wt = max(1, dbg["walker_total"])
 print("  walkers: wait-prev %.1f%% wait-hard %.1f%% | refills %d hard waits %d | cycles per refill %.0f" % (100 * dbg["walker_wait_prev"] / wt, 100 * dbg["walker_wait_hard"] / wt, dbg["walker_refills"] // runs, dbg["walker_hard_waits"] // runs, wt / max(1, dbg["walker_refills"])))
+print("  walkers: steps %.1f%% refills %.1f%% of walker time | general channels %d per run | walker cycles per warp-run %.0f" % (100 * dbg["r13"] / wt, 100 * dbg["r14"] / wt, dbg["r15"] // runs, wt / runs / 512))
 print(f"verts {verts} segment {segment} streams {n} env {{{', '.join(k + '=' + v for k, v in os.environ.items() if k.startswith('MOB200_'))}}}: "
       f"best {ms[0]:.3f} ms median {ms[len(ms)//2]:.3f} ms | decoded {wl['decoded_bytes']/ms[0]/1e6:.0f} GB/s traffic {alg/ms[0]/1e6:.0f} GB/s ({alg/ms[0]/1e6/6543.4:.3f} of peak) parity={ok}", flush=True)
