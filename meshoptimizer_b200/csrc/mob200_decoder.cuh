@@ -190,12 +190,12 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 	const uint32_t my_count = blockIdx.x < T.total_blocks ? (T.total_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 
 	long long dbg_meta = 0, dbg_slot = 0, dbg_look = 0;
-	const long long dbg_t0 = clock64();
+	const long long dbg_t0 = dbg_clock();
 
 	for (uint32_t i0 = 0; i0 < my_count; i0 += kProducerBatch)
 	{
 		// ---- metadata of up to kProducerBatch blocks, one per lane: the dependent global loads of all of them overlap ----
-		const long long c0 = clock64();
+		const long long c0 = dbg_clock();
 		const uint32_t mi = i0 + lane;
 		const bool has = lane < kProducerBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0;
@@ -246,7 +246,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			}
 		}
 		__syncwarp();
-		dbg_meta += clock64() - c0;
+		dbg_meta += dbg_clock() - c0;
 
 		// ---- hand the blocks to the decoders, in order -------------------------------------------------------------
 		const uint32_t in_batch = min(kProducerBatch, my_count - i0);
@@ -263,7 +263,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			const uint8_t* tail = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, m_tail, j));
 
 			// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
-			const long long c1 = clock64();
+			const long long c1 = dbg_clock();
 			mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 2000);
 			if (i >= kSlots && freed < i - (kSlots - 1))
 				freed = i - (kSlots - 1);
@@ -308,7 +308,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 					mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 2000);
 					++freed;
 				}
-				dbg_slot += clock64() - c1;
+				dbg_slot += dbg_clock() - c1;
 				head = start + len;
 				for (uint32_t q = lane; q < nq; q += 32)
 					S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0; // needed by the decoders from the start of the block
@@ -346,7 +346,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			}
 			else
 			{
-				dbg_slot += clock64() - c1;
+				dbg_slot += dbg_clock() - c1;
 				__syncwarp();
 				if (lane == j)
 				{
@@ -358,7 +358,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			}
 
 			// ---- carry into the block, per 4-byte lane ---------------------------------------------------------------
-			const long long c2 = clock64();
+			const long long c2 = dbg_clock();
 			if (valid)
 			{
 				const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
@@ -396,18 +396,20 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(carry_bar + slot);
-			dbg_look += clock64() - c2;
+			dbg_look += dbg_clock() - c2;
 		}
 	}
 
+#ifdef MOB200_DEBUG_COUNTERS
 	if (lane == 0)
 	{
 		unsigned long long* dbg = debug_counters(T);
-		atomicAdd(dbg + kDbgProducerTotal, (unsigned long long)(clock64() - dbg_t0));
+		atomicAdd(dbg + kDbgProducerTotal, (unsigned long long)(dbg_clock() - dbg_t0));
 		atomicAdd(dbg + kDbgProducerMeta, (unsigned long long)dbg_meta);
 		atomicAdd(dbg + kDbgProducerWaitSlot, (unsigned long long)dbg_slot);
 		atomicAdd(dbg + kDbgProducerLookback, (unsigned long long)dbg_look);
 	}
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -416,7 +418,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 
 // one 16-value group -> 16 bytes in registers.  entry = 0: all zero; else (offset << 2) | log2(bits).
 // Groups with all-ones fields take their escape bytes through the thread's 16-byte scratch slot.
-__device__ __forceinline__ uint4 unpack_group(const uint8_t* ring, uint32_t base, uint32_t entry, uint8_t* scratch)
+__device__ __noinline__ uint4 unpack_group(const uint8_t* ring, uint32_t base, uint32_t entry, uint8_t* scratch)
 {
 	uint4 r = make_uint4(0, 0, 0, 0);
 	if (entry == 0)
@@ -521,7 +523,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 	uint8_t* scratch = smem + kSmemPatch + tid * 16;
 	uint32_t tile_uses = 0;
 	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
-	const long long dbg_t0 = clock64();
+	const long long dbg_t0 = dbg_clock();
 
 	for (uint32_t i = 0, t = blockIdx.x; t < T.total_blocks; ++i, t += gridDim.x)
 	{
@@ -530,9 +532,9 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 		const SlotData& S = slots[slot];
 
 		{
-			const long long c0 = clock64();
+			const long long c0 = dbg_clock();
 			mbar_wait(full + slot, phase);
-			dbg_full += clock64() - c0;
+			dbg_full += dbg_clock() - c0;
 		}
 		if (!S.P.valid)
 		{
@@ -647,9 +649,10 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 
 			// scan of the chunk totals across the gstride threads of this lane q (inactive chunks add 0)
 			uint32_t incl = total;
-			for (uint32_t dlt = 1; dlt < gstride; dlt <<= 1)
+#pragma unroll
+			for (uint32_t dlt = 1; dlt < 16; dlt <<= 1)
 			{
-				const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dlt, gstride);
+				const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dlt, 16); // (gstride divides 16: c >= dlt keeps the segments apart)
 				if (c >= dlt)
 					incl = lane_combine(o, incl, H);
 			}
@@ -664,12 +667,12 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 
 			if (base == warp_base)
 			{
-				const long long c0 = clock64();
+				const long long c0 = dbg_clock();
 				mbar_wait(carry_bar + slot, phase);
-				const long long c1 = clock64();
+				const long long c1 = dbg_clock();
 				mbar_wait(tile_free, (tile_uses & 1u) ^ 1u); // every warp has finished storing the previous tile
 				dbg_carry += c1 - c0;
-				dbg_tile += clock64() - c1;
+				dbg_tile += dbg_clock() - c1;
 			}
 
 			if (active)
@@ -739,22 +742,36 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 			if ((oa & 15) == 0)
 			{
 				const uint32_t pieces = nbytes >> 4;
-				for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
+				if (fk == 0)
 				{
-					const uint32_t o = j << 4;
-					const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
-					uint2 lo = p[0], hi = p[1];
-					if (fk == 1)
+#pragma unroll 4
+					for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
 					{
-						lo.x = apply_filter32(lo.x, filter), lo.y = apply_filter32(lo.y, filter);
-						hi.x = apply_filter32(hi.x, filter), hi.y = apply_filter32(hi.y, filter);
+						const uint32_t o = j << 4;
+						const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+						const uint2 lo = p[0], hi = p[1];
+						*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
 					}
-					else if (fk == 2)
+				}
+				else
+				{
+					for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
 					{
-						lo = apply_filter64(lo, filter);
-						hi = apply_filter64(hi, filter);
+						const uint32_t o = j << 4;
+						const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+						uint2 lo = p[0], hi = p[1];
+						if (fk == 1)
+						{
+							lo.x = apply_filter32(lo.x, filter), lo.y = apply_filter32(lo.y, filter);
+							hi.x = apply_filter32(hi.x, filter), hi.y = apply_filter32(hi.y, filter);
+						}
+						else
+						{
+							lo = apply_filter64(lo, filter);
+							hi = apply_filter64(hi, filter);
+						}
+						*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
 					}
-					*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
 				}
 				const uint32_t rem_words = (nbytes & 15u) >> 2;
 				if (tid < rem_words)
@@ -787,14 +804,16 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 			mbar_arrive(tile_free);
 	}
 
+#ifdef MOB200_DEBUG_COUNTERS
 	if (tid == 0)
 	{
 		unsigned long long* dbg = debug_counters(T);
-		atomicAdd(dbg + kDbgDecoderTotal, (unsigned long long)(clock64() - dbg_t0));
+		atomicAdd(dbg + kDbgDecoderTotal, (unsigned long long)(dbg_clock() - dbg_t0));
 		atomicAdd(dbg + kDbgDecoderWaitFull, (unsigned long long)dbg_full);
 		atomicAdd(dbg + kDbgDecoderWaitCarry, (unsigned long long)dbg_carry);
 		atomicAdd(dbg + kDbgDecoderWaitTile, (unsigned long long)dbg_tile);
 	}
+#endif
 }
 
 } // namespace mob200

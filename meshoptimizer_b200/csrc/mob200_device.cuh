@@ -10,6 +10,17 @@ namespace mob200
 // small device helpers
 // ------------------------------------------------------------------------------------------------
 
+// cycle counter for the diagnostic counters (mob200_plan_debug_counters); compiled out unless the library is
+// built with -DMOB200_DEBUG_COUNTERS (MOB200_DEBUG_COUNTERS=1 python -m meshoptimizer_b200.build)
+__device__ __forceinline__ long long dbg_clock()
+{
+#ifdef MOB200_DEBUG_COUNTERS
+	return clock64();
+#else
+	return 0;
+#endif
+}
+
 __device__ __forceinline__ uint32_t smem_addr(const void* p)
 {
 	return (uint32_t)__cvta_generic_to_shared(p);

@@ -118,13 +118,13 @@ __device__ __forceinline__ void walk_wait(WalkWarp& W)
 // `on` lanes take part; the others only keep the warp converged.
 __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, uint32_t lane)
 {
-	const long long dbg_r0 = clock64();
+	const long long dbg_r0 = dbg_clock();
 	W.dbg_refills++;
 	if (W.pending)
 	{
-		const long long c0 = clock64();
+		const long long c0 = dbg_clock();
 		walk_wait(W);
-		W.dbg_wait += clock64() - c0;
+		W.dbg_wait += dbg_clock() - c0;
 	}
 
 	const uint32_t ci = L.rel / kWalkChunkBytes;
@@ -165,9 +165,9 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 		const bool hard = on && min(L.rel + kWalkNeed, L.limit) > safe;
 		if (__any_sync(0xffffffffu, hard))
 		{
-			const long long c0 = clock64();
+			const long long c0 = dbg_clock();
 			walk_wait(W);
-			W.dbg_hard += clock64() - c0;
+			W.dbg_hard += dbg_clock() - c0;
 			W.dbg_hards++;
 			safe = L.issued * kWalkChunkBytes;
 		}
@@ -182,14 +182,7 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 		asm volatile("prefetch.global.L2 [%0];" ::"l"(L.org + L.prefetched));
 		L.prefetched += 128;
 	}
-	W.dbg_refill += clock64() - dbg_r0;
-}
-
-// mid-channel: only when a lane has come within reach of the end of what its ring is known to hold
-__device__ __forceinline__ void walk_refill_if_needed(WalkLane& L, WalkWarp& W, bool on, uint32_t lane)
-{
-	if (__any_sync(0xffffffffu, on && min(L.rel + kWalkNeed, L.limit) > L.safe_end))
-		walk_refill(L, W, on, lane);
+	W.dbg_refill += dbg_clock() - dbg_r0;
 }
 
 __device__ __forceinline__ uint32_t ring_word(const WalkLane& L, uint32_t rel)
@@ -244,7 +237,6 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 	const uint32_t version = L.version;
 	const uint32_t ctrl_bytes = version ? L.vs / 4 : 0;
 	bool bad = false;
-	const bool full_blocks = __all_sync(0xffffffffu, !on || groups == 16);
 
 	if (on && L.rel_end - L.rel < ctrl_bytes)
 		bad = true;
@@ -309,71 +301,56 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 		if (lit && L.rel_end - L.rel < na) // (:1546-1554)
 			bad = true;
 		const bool gon0 = kon && !bad;
-		walk_refill(L, W, gon0, lane); // (literal skips may have moved rel arbitrarily)
 		const bool pk = gon0 && packed;
-		const uint32_t selectors = pk ? ring_u32_at(L, L.rel) : 0u;
-		const uint32_t lutbase = W.lut + (pk ? (version ? 3u + ctrl : 2u) : 0u) * 128u;
-		L.rel += pk ? hdr : 0u;
 
-		// The 16 group steps, branch-free and independent of each other except through L.rel.  The reference
-		// requires 24 readable bytes in front of every group of a bit-packed channel (:1385,:1415); positions only
-		// grow, so the rule holds for all groups iff it holds for the last one (a lane that runs past its input
-		// keeps stepping over stale ring bytes -- memory-safe -- and is rejected below).
-		uint32_t r[8];
-		uint32_t p_last = L.rel;
-		const long long dbg_s0 = clock64();
+		// The 16 group steps in four rounds of four (a rolled loop: the three warp roles share the instruction
+		// cache), branch-free and independent of each other except through L.rel.  The reference requires 24
+		// readable bytes in front of every group of a bit-packed channel (:1385,:1415); positions only grow, so the
+		// rule holds for all groups iff it holds for the last one (a lane that runs past its input keeps stepping
+		// over stale ring bytes -- memory-safe -- and is rejected below).
+		uint32_t sels = 0, lutbase = W.lut, p_last = 0;
+		WalkEntry t;
+		const long long dbg_s0 = dbg_clock();
 		W.dbg_general++;
-		if (full_blocks)
+#pragma unroll 1
+		for (uint32_t gq = 0; gq < 16; gq += 4)
 		{
-			// every lane that is on has 16 groups: fully unrolled, constant shifts.  The shared-memory loads are
-			// volatile and therefore stay in program order: the table entry of group g+1 is requested BEFORE the ring
-			// words of group g, so its latency never sits on the dependent chain of the running offset.
-			WalkEntry t = walk_entry_load(lutbase | ((selectors << 5) & 0x60u));
-#pragma unroll
-			for (uint32_t g = 0; g < 16; ++g)
+			// refill at the start of the channel (literal skips may have moved rel arbitrarily), and in the middle if a
+			// lane has come within reach of the end of what its ring is known to hold
+			if (gq == 0 || (gq == 8 && __any_sync(0xffffffffu, gon0 && min(L.rel + kWalkNeed, L.limit) > L.safe_end)))
+				walk_refill(L, W, gon0, lane);
+			if (gq == 0)
 			{
-				if (g == 8)
-					walk_refill_if_needed(L, W, gon0, lane);
-				WalkEntry nxt = t;
-				if (g + 1 < 16)
-				{
-					const uint32_t h = g + 1;
-					const uint32_t sel32 = h >= 3 ? (selectors >> (2 * h - 5)) : (selectors << (5 - 2 * h)); // selector * 32
-					nxt = walk_entry_load(lutbase | (sel32 & 0x60u));
-				}
-				if (g == 15)
-					p_last = L.rel;
-				const uint32_t e = walk_step(L, t, start);
-				if (g & 1u)
-					r[g >> 1] = __byte_perm(r[g >> 1], e, 0x5410);
-				else
-					r[g >> 1] = e;
+				sels = pk ? ring_u32_at(L, L.rel) : 0u;
+				lutbase = W.lut + (pk ? (version ? 3u + ctrl : 2u) : 0u) * 128u;
+				L.rel += pk ? hdr : 0u;
+				p_last = L.rel;
+				t = walk_entry_load(0 < groups ? lutbase | ((sels << 5) & 0x60u) : W.lut);
+			}
+			// (the shared-memory loads are volatile and stay in program order: the table entry of the next group is
+			// requested before the ring words of the current one, so its latency is off the chain of the running offset)
+			uint32_t e[4];
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j)
+			{
+				const uint32_t nsel = j < 3 ? ((sels >> (2 * (j + 1))) & 3u) : ((sels >> 8) & 3u);
+				const WalkEntry nxt = walk_entry_load(gq + j + 1 < groups ? lutbase + nsel * 32u : W.lut);
+				p_last = gq + j < groups ? L.rel : p_last;
+				e[j] = walk_step(L, t, start);
 				t = nxt;
 			}
+			sels >>= 8;
+			if (gon0 && !lit) // (zero channels store zeros)
+				*reinterpret_cast<uint2*>(rows + (size_t)k * 16 + gq) = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
 		}
-		else
-		{
-			// a partial block (the last one of a stream) somewhere in the warp: rolled loop, entries stored one by one
-#pragma unroll 1
-			for (uint32_t g = 0; g < 16; ++g)
-			{
-				if (g == 8)
-					walk_refill_if_needed(L, W, gon0, lane);
-				const bool has = g < groups;
-				const WalkEntry t = walk_entry_load(has ? lutbase + ((selectors >> (2 * g)) & 3u) * 32u : W.lut);
-				p_last = has ? L.rel : p_last;
-				const uint32_t e = walk_step(L, t, start);
-				if (has && pk)
-					rows[(size_t)k * 16 + g] = (uint16_t)e;
-			}
-		}
-		W.dbg_steps += clock64() - dbg_s0;
+		W.dbg_steps += dbg_clock() - dbg_s0;
 		if (pk && L.rel_end - min(p_last, L.rel_end) < kGroupReadLimit)
 			bad = true;
 		if (lit && !bad)
 		{
 			// literal channel: group g is the 16 raw bytes at rel + 16 g; the channel holds n bytes, not 16 * groups (:1553)
 			const uint32_t e0 = ((L.rel - start) << 2) | 3u;
+			uint32_t r[8];
 #pragma unroll
 			for (uint32_t j = 0; j < 8; ++j)
 			{
@@ -381,21 +358,9 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 				const uint32_t hi = 2 * j + 1 < groups ? e0 + (16u << 2) * (2 * j + 1) : 0u;
 				r[j] = lo | (hi << 16);
 			}
-			L.rel += n;
-		}
-
-		if (kon && !bad && (full_blocks || lit || !pk))
-		{
-			if (!full_blocks && !lit)
-			{
-				// zero channel of a partial block
-#pragma unroll
-				for (uint32_t j = 0; j < 8; ++j)
-					r[j] = 0;
-			}
 			row[0] = make_uint4(r[0], r[1], r[2], r[3]);
-			if (groups > 8)
-				row[1] = make_uint4(r[4], r[5], r[6], r[7]);
+			row[1] = make_uint4(r[4], r[5], r[6], r[7]);
+			L.rel += n;
 		}
 	}
 	return !bad;
@@ -519,7 +484,7 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 	W.dbg_steps = W.dbg_refill = 0;
 	W.dbg_general = 0;
 	W.dbg_refills = W.dbg_hards = 0;
-	const long long dbg_t0 = clock64();
+	const long long dbg_t0 = dbg_clock();
 	walk_lut_init(region + kWalkSmemLut, lane);
 	__syncwarp();
 
@@ -534,10 +499,11 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 		walk_stream_group(T, W, base, lane, ring_smem);
 		__syncwarp();
 	}
+#ifdef MOB200_DEBUG_COUNTERS
 	if (lane == 0)
 	{
 		unsigned long long* dbg = reinterpret_cast<unsigned long long*>(T.counters + 16);
-		atomicAdd(dbg + 8, (unsigned long long)(clock64() - dbg_t0));
+		atomicAdd(dbg + 8, (unsigned long long)(dbg_clock() - dbg_t0));
 		atomicAdd(dbg + 9, (unsigned long long)W.dbg_wait);
 		atomicAdd(dbg + 10, (unsigned long long)W.dbg_hard);
 		atomicAdd(dbg + 11, (unsigned long long)W.dbg_refills);
@@ -546,6 +512,7 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 		atomicAdd(dbg + 14, (unsigned long long)W.dbg_refill);
 		atomicAdd(dbg + 15, (unsigned long long)W.dbg_general);
 	}
+#endif
 }
 
 } // namespace mob200
