@@ -271,7 +271,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 		d.nblocks = nblocks[order[i]];
 		d.vertex_size = (uint16_t)s.vertex_size;
 		d.filter = (uint8_t)s.filter;
-		d.reserved = 0;
+		d.block_groups = (uint8_t)(block_vertices((uint32_t)s.vertex_size) / kGroup);
 		d.caller_index = order[i];
 		total_blocks += d.nblocks;
 		total_chan += (uint64_t)d.nblocks * s.vertex_size;
@@ -422,14 +422,15 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 	if (set_device(plan->ctx))
 		return MOB200_ERR_CUDA;
 	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-	if (plan->T.walker_lead != kDecodeOnly || plan->runs == 0) // (decode-only diagnostic: reuse the tables of the first run)
+	const bool reuse_tables = plan->T.walker_lead == kDecodeOnly || plan->T.walker_lead == kRewalk;
+	if (!reuse_tables || plan->runs == 0) // (decode-only diagnostics: reuse the tables of the first run)
 	{
 		plan->T.epoch = (plan->T.epoch + 1) & 0x3fffffffu;
 		if (plan->T.epoch == 0)
 			plan->T.epoch = 1;
 	}
 	DevTables T = plan->T;
-	if (T.walker_lead == kDecodeOnly && plan->runs == 0)
+	if (reuse_tables && plan->runs == 0)
 		T.walker_lead = 0; // the first run builds the tables
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];

@@ -63,7 +63,7 @@ struct DevStream
 	uint32_t nblocks;
 	uint16_t vertex_size;
 	uint8_t filter;        // enum mob200_Filter
-	uint8_t reserved;
+	uint8_t block_groups;  // vertices per block / 16 (block_vertices(vertex_size): spares the kernels an integer division)
 	uint32_t caller_index; // position of the stream in the caller's array (status is reported there)
 };
 

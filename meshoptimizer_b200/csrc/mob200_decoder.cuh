@@ -211,7 +211,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			m_vs = vs;
 			m_b = b;
 			m_filter = d->filter;
-			const uint32_t bv = block_vertices(vs);
+			const uint32_t bv = d->block_groups * kGroup;
 			m_n = min(bv, d->vertex_count - b * bv);
 			m_out = reinterpret_cast<unsigned long long>(d->dst + (uint64_t)b * bv * vs);
 			m_rows = reinterpret_cast<unsigned long long>(T.group_table + (d->chan_base + (uint64_t)b * vs) * 16);
@@ -243,6 +243,32 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 				m_lo = lo;
 				m_enc = (uint32_t)(hi - lo);
 				m_shift = (uint32_t)(a0 - lo);
+			}
+		}
+		// channel bytes (lane j, up to 8 of them) and the look-back entries of the predecessor block (four lanes
+		// per block, two 4-byte lanes each) are requested here as well: all of it is in flight together, and the
+		// per-block part below carries no global-memory latency when the predecessor has already been decoded
+		uint32_t m_ch_lo = 0, m_ch_hi = 0;
+		if (m_valid && m_version && m_vs <= 32)
+		{
+			const uint8_t* ch = reinterpret_cast<const uint8_t*>(m_tail) + m_vs;
+			const uint32_t nqj = m_vs >> 2;
+			m_ch_lo = ldg_u32_at(ch, min(nqj, 4u)) & (nqj >= 4 ? 0xffffffffu : ((1u << (8 * nqj)) - 1u));
+			if (nqj > 4)
+				m_ch_hi = ldg_u32_at(ch + 4, nqj - 4) & (nqj >= 8 ? 0xffffffffu : ((1u << (8 * (nqj - 4))) - 1u));
+		}
+		unsigned long long pre0 = 0, pre1 = 0;
+		{
+			const uint32_t tj = lane >> 2, q0 = (lane & 3u) * 2u;
+			const uint32_t pv = __shfl_sync(0xffffffffu, m_valid, tj), pvs = __shfl_sync(0xffffffffu, m_vs, tj), pb = __shfl_sync(0xffffffffu, m_b, tj);
+			const unsigned long long* plook = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, tj));
+			const uint32_t pnq = pvs >> 2;
+			if (pv && pb > 0 && pnq <= 8)
+			{
+				if (q0 < pnq)
+					pre0 = ld_volatile_u64(plook + q0 - pnq);
+				if (q0 + 1 < pnq)
+					pre1 = ld_volatile_u64(plook + q0 + 1 - pnq);
 			}
 		}
 		__syncwarp();
@@ -310,8 +336,15 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 				}
 				dbg_slot += dbg_clock() - c1;
 				head = start + len;
-				for (uint32_t q = lane; q < nq; q += 32)
-					S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0; // needed by the decoders from the start of the block
+				// channel bytes: needed by the decoders from the start of the block
+				if (nq <= 8)
+				{
+					if (lane == j)
+						*reinterpret_cast<uint2*>(S.channels) = make_uint2(m_ch_lo, m_ch_hi);
+				}
+				else
+					for (uint32_t q = lane; q < nq; q += 32)
+						S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0;
 				__syncwarp();
 				if (lane == j)
 				{
@@ -359,7 +392,25 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 
 			// ---- carry into the block, per 4-byte lane ---------------------------------------------------------------
 			const long long c2 = dbg_clock();
-			if (valid)
+			bool carry_done = false;
+			if (valid && b > 0 && nq <= 8)
+			{
+				// the prefetched look-back entries: good if every one of them is an inclusive prefix of this run
+				const bool mine = (lane >> 2) == j;
+				const uint32_t q0 = (lane & 3u) * 2u;
+				const uint32_t f0 = (uint32_t)(pre0 >> 32), f1 = (uint32_t)(pre1 >> 32);
+				const uint32_t want_flag = ((T.epoch & 0x3fffffffu) << 2) | 2u;
+				const bool good = (q0 >= nq || f0 == want_flag) && (q0 + 1 >= nq || f1 == want_flag);
+				carry_done = __all_sync(0xffffffffu, !mine || good);
+				if (carry_done && mine)
+				{
+					if (q0 < nq)
+						S.carry[q0] = (uint32_t)pre0;
+					if (q0 + 1 < nq)
+						S.carry[q0 + 1] = (uint32_t)pre1;
+				}
+			}
+			if (valid && !carry_done)
 			{
 				const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
 				for (uint32_t q = lane; q < nq; q += 32)

@@ -24,6 +24,7 @@ constexpr int kCtaThreads = kDecodeThreads + kProducerThreads + kWalkerThreads;
 constexpr int kCtasPerSm = 5;        // register budget: 65536 / (5 x 192) -> 64 registers per thread
 
 constexpr uint32_t kWalkOnly = 0xffffffffu;   // DevTables::walker_lead: decoders off (diagnostic)
+constexpr uint32_t kRewalk = 0xfffffffdu;     // DevTables::walker_lead: like kDecodeOnly but the walkers run as well (contention without dependency; diagnostic)
 constexpr uint32_t kDecodeOnly = 0xfffffffeu; // DevTables::walker_lead: walkers off, tables of the previous run are reused (diagnostic)
 
 uint32_t decode_smem_bytes();

@@ -378,7 +378,7 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 	const uint32_t size = have ? d->src_size : 0;
 	L.vs = d->vertex_size;
 	L.count = d->vertex_count;
-	L.bv = block_vertices(L.vs);
+	L.bv = d->block_groups * kGroup;
 	L.nblocks = have ? d->nblocks : 0;
 	L.version = 0;
 	L.status = 0;

@@ -136,7 +136,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 	const uint32_t size = d->src_size;
 	const uint32_t vs = d->vertex_size;
 	const uint32_t count = d->vertex_count;
-	const uint32_t bv = block_vertices(vs);
+	const uint32_t bv = d->block_groups * kGroup;
 	const uint32_t nblocks = d->nblocks;
 
 	uint32_t* boff = T.block_offset + d->block_base + s;
