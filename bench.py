@@ -7,7 +7,7 @@ Workload (N=1): BASELINE.json configs[1] -- the v1 codec at encode level 2 on a 
 32-byte-per-vertex data set (2.147 GB decoded), produced by the UNMODIFIED reference encoder
 (oracle/_ref) as independently encoded buffer ranges of `--segment` vertices each (SURVEY.md section
 7.3 H1: a stream carries no block index, so the parallel unit is the independently encoded stream).
-A "step" is one pass of the hot path (walk + decode kernels) over the whole batch.
+A "step" is one pass of the hot path (one persistent kernel: walker, producer and decoder warps) over the whole batch.
 
   value     decoded GB/s, inputs and outputs resident in HBM, CUDA events on the launching stream,
             max over ranks, K steps back to back after W warm-up steps (working set >> L2)
@@ -299,7 +299,14 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (decode_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # DRAM bytes of one launch of this workload, from the committed ncu --set full capture (profiles/): not measured live
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        for rec in json.load(open(tpath)):
+            if rec.get("verts") == args.verts and rec.get("segment") == args.segment and rec.get("level") == args.level and rec.get("version") == args.version:
+                traffic, traffic_src = rec["dram_bytes_per_launch"], rec.get("source")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
                 "kernel": "decode_kernel", "kernel_ms": decode_ms, "walk_kernel_ms": walk_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
@@ -347,7 +354,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, wl), "clocks": clocks, "e2e": e2e, "gpu_launches": int(args.steps * plan_launches),
             "roofline": roofline, "cpu_baseline": cpu,
-            "notes": {"generation_seconds": t_gen, "kernels_per_step": ["decode_kernel (fused walker + decoder warps)"]},
+            "notes": {"generation_seconds": t_gen, "kernels_per_step": ["decode_kernel (one persistent kernel: walker, producer and decoder warps)"]},
         }
         print(json.dumps(line))
     if world > 1:

@@ -76,7 +76,7 @@ struct DevTables
 	                              // by the walker warps, read by the decoders.
 	uint16_t* group_table;        // per (block, byte-channel): 16 entries, one per 16-value group:
 	                              // 0 = all zero, else (offset_in_block << 2) | log2(bits).  Walker -> decoder.
-	unsigned long long* progress; // [n_streams]: epoch << 32 | number of blocks walked (release/acquire)
+	unsigned long long* progress; // [n_streams]: epoch << 32 | codec version << 31 | number of blocks walked (release/acquire)
 	unsigned long long* lookback; // per block, vertex_size/4 entries: (epoch << 2 | state) << 32 | value
 	const uint2* ticket_info;     // [total_blocks]: decode order -> (stream, block)
 	const uint32_t* block_ticket; // [total_blocks]: global block id -> position in the decode order

@@ -115,17 +115,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	}
 }
 
-// same for waits that are expected to be long: the thread may stay suspended for up to `ns` per attempt
+// same for waits that are expected to be long (the producer waiting for a slot: a block takes the decoders a
+// few microseconds): sleep between attempts instead of spinning on issue slots the decoders need
 __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity, uint32_t ns)
 {
-	uint32_t ok;
-	do
-	{
-		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-		             : "=r"(ok)
-		             : "r"(smem_addr(bar)), "r"(parity), "r"(ns)
-		             : "memory");
-	} while (!ok);
+	while (!mbar_try_wait(bar, parity))
+		__nanosleep(ns);
 }
 
 // byte-lane helpers (channel mode 0) and 16-bit / xor helpers (modes 1, 2)
@@ -154,7 +149,7 @@ __device__ __forceinline__ uint32_t sum_bytes(const uint4& v)
 // producer warp
 // ------------------------------------------------------------------------------------------------
 
-constexpr uint32_t kProducerBatch = 8; // blocks whose metadata chains (ticket -> stream -> progress -> offsets) are in flight together, one per lane
+constexpr uint32_t kProducerBatch = 16;// blocks whose metadata chains (ticket -> stream -> progress -> offsets) are in flight together, one per lane
 
 // debug counters (cycles, summed over CTAs): see mob200_plan_debug_counters
 enum
@@ -196,17 +191,26 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 	{
 		// ---- metadata of up to kProducerBatch blocks, one per lane: the dependent global loads of all of them overlap ----
 		const long long c0 = dbg_clock();
+		// level 1: ticket -> (stream, block); level 2: stream descriptor + walker progress (which also carries the codec
+		// version); level 3: block byte range, channel bytes, and -- four entries per lane, two lanes per block -- the
+		// look-back entries of the predecessor block.  Everything of one level is requested before any of it is used.
 		const uint32_t mi = i0 + lane;
 		const bool has = lane < kProducerBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0;
 		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
+		const uint32_t* boff = nullptr;
+		const uint8_t* src = nullptr;
+		uint32_t src_size = 0;
 		if (has)
 		{
 			const uint32_t t = blockIdx.x + mi * gridDim.x;
 			const uint2 info = __ldg(T.ticket_info + t);
 			const uint32_t s = info.x, b = info.y;
 			const DevStream* d = T.streams + s;
-			const uint8_t* src = d->src;
+			const unsigned long long* progress = T.progress + s;
+			unsigned long long pv = ld_acquire_u64(progress);
+			src = d->src;
+			src_size = d->src_size;
 			const uint32_t vs = d->vertex_size;
 			m_vs = vs;
 			m_b = b;
@@ -216,25 +220,59 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			m_out = reinterpret_cast<unsigned long long>(d->dst + (uint64_t)b * bv * vs);
 			m_rows = reinterpret_cast<unsigned long long>(T.group_table + (d->chan_base + (uint64_t)b * vs) * 16);
 			m_look = reinterpret_cast<unsigned long long>(T.lookback + (d->chan_base >> 2) + (uint64_t)b * (vs >> 2));
+			boff = T.block_offset + d->block_base + s + b;
 
 			// wait until the walker has published this block (back-off: a starved producer must not take issue
 			// slots from the walker warps)
-			const unsigned long long* progress = T.progress + s;
-			for (uint32_t ns = 32;;)
+			for (uint32_t ns = 32; (uint32_t)(pv >> 32) != T.epoch || ((uint32_t)pv & 0x7fffffffu) <= b;)
 			{
-				unsigned long long v = ld_acquire_u64(progress);
-				if ((uint32_t)(v >> 32) == T.epoch && (uint32_t)v > b)
-					break;
 				__nanosleep(ns);
 				ns = ns < 1024 ? ns * 2 : ns;
+				pv = ld_acquire_u64(progress);
 			}
-			const uint32_t* boff = T.block_offset + d->block_base + s + b;
+			m_version = ((uint32_t)pv >> 31) & 1u;
+		}
+		__syncwarp();
+
+		unsigned long long pre0 = 0, pre1 = 0, pre2 = 0, pre3 = 0;
+		{
+			const uint32_t tj = lane >> 1, q0 = (lane & 1u) * 4u;
+			const uint32_t pvs = __shfl_sync(0xffffffffu, m_vs, tj), pb = __shfl_sync(0xffffffffu, m_b, tj);
+			const unsigned long long* plook = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, tj));
+			const uint32_t pnq = pvs >> 2;
+			if (plook && pb > 0 && pnq <= 8)
+			{
+				// (a block that turns out not to be decodable has a decodable predecessor or none: the entries exist)
+				const unsigned long long* e = plook + q0 - pnq;
+				if (q0 < pnq)
+					pre0 = ld_volatile_u64(e);
+				if (q0 + 1 < pnq)
+					pre1 = ld_volatile_u64(e + 1);
+				if (q0 + 2 < pnq)
+					pre2 = ld_volatile_u64(e + 2);
+				if (q0 + 3 < pnq)
+					pre3 = ld_volatile_u64(e + 3);
+			}
+		}
+		uint32_t m_ch_lo = 0, m_ch_hi = 0;
+		if (has)
+		{
 			const uint32_t off = __ldcg(boff), end = __ldcg(boff + 1);
+			const uint32_t vs = m_vs;
+			const uint8_t* tail = src + src_size - tail_bytes(vs, m_version);
+			if (m_version && vs <= 32 && src_size >= tail_bytes(vs, m_version))
+			{
+				// channel bytes (up to 8); harmless for a stream whose walk failed: the tail lies inside the input
+				const uint8_t* ch = tail + vs;
+				const uint32_t nqj = vs >> 2;
+				m_ch_lo = ldg_u32_at(ch, min(nqj, 4u)) & (nqj >= 4 ? 0xffffffffu : ((1u << (8 * nqj)) - 1u));
+				if (nqj > 4)
+					m_ch_hi = ldg_u32_at(ch + 4, nqj - 4) & (nqj >= 8 ? 0xffffffffu : ((1u << (8 * (nqj - 4))) - 1u));
+			}
 			if (off != kInvalidOffset && end != kInvalidOffset)
 			{
 				m_valid = 1;
-				m_version = __ldg(src) & 0x0fu;
-				m_tail = reinterpret_cast<unsigned long long>(src + d->src_size - tail_bytes(vs, m_version));
+				m_tail = reinterpret_cast<unsigned long long>(tail);
 				// 16-byte aligned window around [off, end)
 				const uintptr_t a0 = reinterpret_cast<uintptr_t>(src) + off;
 				const uintptr_t a1 = reinterpret_cast<uintptr_t>(src) + end;
@@ -243,32 +281,6 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 				m_lo = lo;
 				m_enc = (uint32_t)(hi - lo);
 				m_shift = (uint32_t)(a0 - lo);
-			}
-		}
-		// channel bytes (lane j, up to 8 of them) and the look-back entries of the predecessor block (four lanes
-		// per block, two 4-byte lanes each) are requested here as well: all of it is in flight together, and the
-		// per-block part below carries no global-memory latency when the predecessor has already been decoded
-		uint32_t m_ch_lo = 0, m_ch_hi = 0;
-		if (m_valid && m_version && m_vs <= 32)
-		{
-			const uint8_t* ch = reinterpret_cast<const uint8_t*>(m_tail) + m_vs;
-			const uint32_t nqj = m_vs >> 2;
-			m_ch_lo = ldg_u32_at(ch, min(nqj, 4u)) & (nqj >= 4 ? 0xffffffffu : ((1u << (8 * nqj)) - 1u));
-			if (nqj > 4)
-				m_ch_hi = ldg_u32_at(ch + 4, nqj - 4) & (nqj >= 8 ? 0xffffffffu : ((1u << (8 * (nqj - 4))) - 1u));
-		}
-		unsigned long long pre0 = 0, pre1 = 0;
-		{
-			const uint32_t tj = lane >> 2, q0 = (lane & 3u) * 2u;
-			const uint32_t pv = __shfl_sync(0xffffffffu, m_valid, tj), pvs = __shfl_sync(0xffffffffu, m_vs, tj), pb = __shfl_sync(0xffffffffu, m_b, tj);
-			const unsigned long long* plook = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, tj));
-			const uint32_t pnq = pvs >> 2;
-			if (pv && pb > 0 && pnq <= 8)
-			{
-				if (q0 < pnq)
-					pre0 = ld_volatile_u64(plook + q0 - pnq);
-				if (q0 + 1 < pnq)
-					pre1 = ld_volatile_u64(plook + q0 + 1 - pnq);
 			}
 		}
 		__syncwarp();
@@ -290,7 +302,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 
 			// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
 			const long long c1 = dbg_clock();
-			mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 2000);
+			mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 400);
 			if (i >= kSlots && freed < i - (kSlots - 1))
 				freed = i - (kSlots - 1);
 
@@ -331,7 +343,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 						start = head;
 						break;
 					}
-					mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 2000);
+					mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 400);
 					++freed;
 				}
 				dbg_slot += dbg_clock() - c1;
@@ -396,11 +408,11 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 			if (valid && b > 0 && nq <= 8)
 			{
 				// the prefetched look-back entries: good if every one of them is an inclusive prefix of this run
-				const bool mine = (lane >> 2) == j;
-				const uint32_t q0 = (lane & 3u) * 2u;
-				const uint32_t f0 = (uint32_t)(pre0 >> 32), f1 = (uint32_t)(pre1 >> 32);
+				const bool mine = (lane >> 1) == j;
+				const uint32_t q0 = (lane & 1u) * 4u;
 				const uint32_t want_flag = ((T.epoch & 0x3fffffffu) << 2) | 2u;
-				const bool good = (q0 >= nq || f0 == want_flag) && (q0 + 1 >= nq || f1 == want_flag);
+				const bool good = (q0 >= nq || (uint32_t)(pre0 >> 32) == want_flag) && (q0 + 1 >= nq || (uint32_t)(pre1 >> 32) == want_flag) &&
+				                  (q0 + 2 >= nq || (uint32_t)(pre2 >> 32) == want_flag) && (q0 + 3 >= nq || (uint32_t)(pre3 >> 32) == want_flag);
 				carry_done = __all_sync(0xffffffffu, !mine || good);
 				if (carry_done && mine)
 				{
@@ -408,6 +420,10 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 						S.carry[q0] = (uint32_t)pre0;
 					if (q0 + 1 < nq)
 						S.carry[q0 + 1] = (uint32_t)pre1;
+					if (q0 + 2 < nq)
+						S.carry[q0 + 2] = (uint32_t)pre2;
+					if (q0 + 3 < nq)
+						S.carry[q0 + 3] = (uint32_t)pre3;
 				}
 			}
 			if (valid && !carry_done)
@@ -733,26 +749,13 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 					st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
 				uint32_t v = lane_combine(carry, excl, H);
 				uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
-				if ((channel & 3u) == 0)
-				{
+				// one instruction stream for the three channel modes: a warp whose two lanes differ in mode does not run it twice
 #pragma unroll
-					for (int j = 0; j < 16; ++j)
-					{
-						v = add8x4(v, w[j]);
-						*reinterpret_cast<uint32_t*>(col) = v;
-						col += vs;
-					}
-				}
-				else
+				for (int j = 0; j < 16; ++j)
 				{
-					const uint32_t X = (channel & 3u) == 2 ? 0xffffffffu : 0u;
-#pragma unroll
-					for (int j = 0; j < 16; ++j)
-					{
-						v = combine16(v, w[j], X);
-						*reinterpret_cast<uint32_t*>(col) = v;
-						col += vs;
-					}
+					v = lane_combine(v, w[j], H);
+					*reinterpret_cast<uint32_t*>(col) = v;
+					col += vs;
 				}
 			}
 		}

@@ -443,7 +443,7 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 			{
 				boff[b + 1] = L.rel - L.rel0;
 				done = b + 1;
-				st_release_u64(progress, tag | done);
+				st_release_u64(progress, tag | (L.version << 31) | done);
 			}
 			else
 			{

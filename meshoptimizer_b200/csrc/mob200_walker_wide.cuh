@@ -339,7 +339,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 			{
 				boff[b + 1] = rel - rel0;
 				__threadfence(); // the table rows were written by other lanes: order them before the release below
-				st_release_u64(progress, tag | done);
+				st_release_u64(progress, tag | (version << 31) | done);
 			}
 		}
 		asm volatile("cp.async.wait_all;" ::: "memory");
