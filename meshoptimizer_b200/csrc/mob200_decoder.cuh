@@ -687,23 +687,29 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 
 				if (!bytes)
 				{
-					// 16-bit deltas: un-zigzag per half word; xor: rotate.  r = ((t >> s1) & M) ^ ((t & L) * 0xffff), t = rotl(x, rot)
-					const bool xr = (channel & 3u) == 2;
-					const uint32_t rot = xr ? (32u - (channel >> 4)) & 31u : 0u;
-					const uint32_t s1 = xr ? 0u : 1u;
-					const uint32_t M = xr ? 0xffffffffu : 0x7fff7fffu;
-					const uint32_t L = xr ? 0u : 0x00010001u;
-					const uint32_t X = xr ? 0xffffffffu : 0u;
-#pragma unroll
-					for (int j = 0; j < 16; ++j)
+					if ((channel & 3u) == 1)
 					{
-						const uint32_t x = __funnelshift_l(w[j], w[j], rot);
-						w[j] = ((x >> s1) & M) ^ ((x & L) * 0xffffu);
-					}
-					total = w[0];
+						// 16-bit deltas: un-zigzag per half word, totals with two-lane adds (VIADD.16x2)
 #pragma unroll
-					for (int j = 1; j < 16; ++j)
-						total = combine16(total, w[j], X);
+						for (int j = 0; j < 16; ++j)
+							w[j] = ((w[j] >> 1) & 0x7fff7fffu) ^ ((w[j] & 0x00010001u) * 0xffffu);
+						total = w[0];
+#pragma unroll
+						for (int j = 1; j < 16; ++j)
+							total = __vadd2(total, w[j]);
+					}
+					else
+					{
+						// xor deltas: rotate right by the channel's amount
+						const uint32_t rot = (32u - (channel >> 4)) & 31u;
+#pragma unroll
+						for (int j = 0; j < 16; ++j)
+							w[j] = __funnelshift_l(w[j], w[j], rot);
+						total = w[0];
+#pragma unroll
+						for (int j = 1; j < 16; ++j)
+							total ^= w[j];
+					}
 				}
 			}
 			else
