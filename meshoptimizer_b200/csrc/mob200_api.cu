@@ -285,7 +285,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->ctx = ctx;
 	plan->n = n;
 
-	uint64_t resident = (uint64_t)ctx->sm_count * ctx->decode_ctas_per_sm;
+	uint64_t resident = (uint64_t)ctx->sm_count * ctx->decode_ctas_per_sm * kUnitsPerCta; // decode units (mob200_kernels.h)
 	uint64_t wanted = std::max<uint64_t>(total_blocks, (n + 31) / 32);
 	plan->grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(wanted, resident));
 
@@ -355,6 +355,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.counters = reinterpret_cast<uint32_t*>(base + off_counters);
 	plan->T.n_streams = (uint32_t)n;
 	plan->T.total_blocks = (uint32_t)total_blocks;
+	plan->T.units = plan->grid;
 	plan->T.epoch = 0;
 	plan->T.walker_lead = ctx->walker_lead;
 	// few streams: one walker WARP per stream (6x lower latency per block); many: one lane per stream
@@ -440,7 +441,10 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 		CUDA_TRY(cudaEventRecord(ev[0], st));
 		CUDA_TRY(cudaEventRecord(ev[1], st)); // (kept for the timing interface: the walk is fused into the decode kernel)
 	}
-	CUDA_TRY(launch_decode(T, plan->grid, st));
+	// unit u runs in CTA u % ctas: a batch with few units still spreads over all SMs
+	const uint32_t ctas_max = (uint32_t)(plan->ctx->sm_count * plan->ctx->decode_ctas_per_sm);
+	const uint32_t ctas = std::max<uint32_t>((plan->grid + kUnitsPerCta - 1) / kUnitsPerCta, std::min<uint32_t>(ctas_max, plan->grid));
+	CUDA_TRY(launch_decode(T, ctas, st));
 	if (timed)
 		CUDA_TRY(cudaEventRecord(ev[2], st));
 	plan->runs++;

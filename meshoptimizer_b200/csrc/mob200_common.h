@@ -84,6 +84,7 @@ struct DevTables
 	uint32_t* counters;           // [0] decode ticket, [1] walker stream ticket, [2] finished roles
 	uint32_t n_streams;
 	uint32_t total_blocks;
+	uint32_t units;               // decode units that take part in this run (unit u decodes tickets u, u + units, ...)
 	uint32_t epoch;               // changes every run, so progress / look-back entries never need clearing
 	uint32_t walker_lead;         // 0xffffffff = walk-only diagnostic mode (decoders off); otherwise unused
 	uint32_t wide_walk;           // 1: one warp per stream (few streams), 0: one lane per stream (many streams)

@@ -1,6 +1,6 @@
 // mob200_decoder.cuh -- phases 2+3 of the decode path: the producer warp and the decoder warps of a CTA.
 //
-// A CTA decodes the blocks  t = blockIdx.x, blockIdx.x + gridDim.x, ...  of the level-major decode order
+// A unit (mob200_kernels.h) decodes the blocks  t = unit, unit + units, ...  of the level-major decode order
 // (block b of every stream before block b+1 of any: the order in which the walkers publish them).
 //
 //   producer warp   runs ahead of the decoders by up to kSlots blocks.  Per block: ticket -> (stream, block),
@@ -72,7 +72,9 @@ constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[k
 constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;    // producer-private: ring_start[kSlots], ring_len[kSlots]
 constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
 constexpr uint32_t kSmemWalkerBytes = 32 * 512 + 6 * 4 * 32 + 16;                  // = kWalkSmemBytes (mob200_walker.cuh) >= kWideSmemBytes
-constexpr uint32_t kSmemTotal = kSmemWalker + kSmemWalkerBytes;
+constexpr uint32_t kSmemTotal = (kSmemWalker + kSmemWalkerBytes + 1023) & ~1023u; // one unit
+constexpr uint32_t kSmemCta = kSmemTotal * kUnitsPerCta;
+static_assert(kSmemCta <= 227 * 1024, "shared memory of one CTA");
 
 static_assert(sizeof(BlockParams) == 80 && sizeof(SlotData) == 416, "SlotData layout");
 static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs, "staging ring must hold the largest block");
@@ -80,7 +82,7 @@ static_assert((kTileBytes & 15) == 0 && (kSmemTile & 15) == 0 && (kSmemPatch & 1
 
 uint32_t decode_smem_bytes()
 {
-	return kSmemTotal;
+	return kSmemCta;
 }
 
 __device__ __forceinline__ uint32_t magic_for(uint32_t d)
@@ -169,7 +171,7 @@ __device__ __forceinline__ unsigned long long* debug_counters(const DevTables& T
 	return reinterpret_cast<unsigned long long*>(T.counters + 16);
 }
 
-__device__ void producer_main(const DevTables& T, uint8_t* smem)
+__device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t unit)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	uint8_t* ring = smem + kSmemStage;
@@ -182,7 +184,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 
 	uint32_t head = 0;  // next free byte of the staging ring
 	uint32_t freed = 0; // blocks [freed, i) of this CTA's sequence are in flight (their ring pieces are live)
-	const uint32_t my_count = blockIdx.x < T.total_blocks ? (T.total_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+	const uint32_t my_count = unit < T.total_blocks ? (T.total_blocks - unit + T.units - 1) / T.units : 0u;
 
 	long long dbg_meta = 0, dbg_slot = 0, dbg_look = 0;
 	const long long dbg_t0 = dbg_clock();
@@ -203,7 +205,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem)
 		uint32_t src_size = 0;
 		if (has)
 		{
-			const uint32_t t = blockIdx.x + mi * gridDim.x;
+			const uint32_t t = unit + mi * T.units;
 			const uint2 info = __ldg(T.ticket_info + t);
 			const uint32_t s = info.x, b = info.y;
 			const DevStream* d = T.streams + s;
@@ -574,7 +576,7 @@ __device__ __noinline__ uint4 unpack_group(const uint8_t* ring, uint32_t base, u
 	return r;
 }
 
-__device__ void decoder_main(const DevTables& T, uint8_t* smem)
+__device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t unit, const uint32_t tid, const uint32_t bar_id)
 {
 	uint8_t* ring = smem + kSmemStage;
 	uint8_t* tile = smem + kSmemTile;
@@ -584,7 +586,6 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 	uint64_t* empty = carry_bar + kSlots;
 	uint64_t* tile_free = empty + kSlots;
 
-	const uint32_t tid = threadIdx.x;
 	const uint32_t lane = tid & 31u;
 	const uint32_t warp_base = tid & ~31u;
 	uint8_t* scratch = smem + kSmemPatch + tid * 16;
@@ -592,7 +593,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
 	const long long dbg_t0 = dbg_clock();
 
-	for (uint32_t i = 0, t = blockIdx.x; t < T.total_blocks; ++i, t += gridDim.x)
+	for (uint32_t i = 0, t = unit; t < T.total_blocks; ++i, t += T.units)
 	{
 		const uint32_t slot = i & (kSlots - 1);
 		const uint32_t phase = (i / kSlots) & 1u;
@@ -772,7 +773,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 		if (lane == 0)
 			mbar_arrive(empty + slot);
 
-		decoder_sync(); // the tile is complete
+		decoder_sync(bar_id); // the tile is complete
 
 		// ---- tile -> global memory, decode filter on the way out ---------------------------------------------------------
 		{
@@ -796,7 +797,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem)
 						uint2* e = reinterpret_cast<uint2*>(tile + tile_offset(r, vs));
 						*e = apply_filter64(*e, filter);
 					}
-				decoder_sync();
+				decoder_sync(bar_id);
 				fk = 0;
 			}
 			if ((oa & 15) == 0)

@@ -64,10 +64,10 @@ __device__ __forceinline__ void fence_proxy_async()
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// barrier among the decoder warps only (the walker warp never takes part)
-__device__ __forceinline__ void decoder_sync()
+// barrier among the decoder warps of one unit (named barrier 1 + unit index in the CTA)
+__device__ __forceinline__ void decoder_sync(uint32_t bar_id)
 {
-	asm volatile("bar.sync 1, %0;" ::"n"(kDecodeThreads) : "memory");
+	asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(kDecodeThreads) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p)

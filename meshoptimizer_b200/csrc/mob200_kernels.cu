@@ -1,6 +1,7 @@
 // mob200_kernels.cu -- sm_100a kernels of the vertex-buffer decode path.
 //
-// One persistent kernel, two warp roles per CTA (north_star phases 1-3):
+// One persistent kernel, one CTA per SM, five units of three warp roles each per CTA (SURVEY.md section 7.4,
+// north_star phases 1-3):
 //
 //   walker warp    phase 1.  One LANE per stream walks the group headers (the stream stores no index:
 //                  reference src/vertexcodec.cpp:1375-1425,1531-1568,1857-1866 advance a single
@@ -35,16 +36,31 @@ namespace mob200
 static_assert(kSmemWalkerBytes >= kWalkSmemBytes && kSmemWalkerBytes >= kWideSmemBytes, "walker shared-memory region");
 
 template <bool kWideWalk>
-__global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) decode_kernel(DevTables T)
+__global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 {
-	extern __shared__ __align__(1024) uint8_t smem[];
+	extern __shared__ __align__(1024) uint8_t smem_all[];
 
 	const bool decode_on = T.walker_lead != kWalkOnly;
 	const bool walk_on = T.walker_lead != kDecodeOnly;
 
+	// role and unit of this warp: decoder warps of unit 0..4, then the producers, then the walkers
+	const uint32_t tid = threadIdx.x;
+	uint32_t role, g, utid;
+	if (tid < kFirstProducerThread)
+		role = 0, g = tid / kDecodeThreads, utid = tid % kDecodeThreads;
+	else if (tid < kFirstWalkerThread)
+		role = 1, g = (tid - kFirstProducerThread) / kProducerThreads, utid = tid % kProducerThreads;
+	else
+		role = 2, g = (tid - kFirstWalkerThread) / kWalkerThreads, utid = tid % kWalkerThreads;
+	// units of one CTA are far apart in the decode order (unit = g * gridDim.x + blockIdx.x): a batch with fewer
+	// units than the device could hold still spreads over all SMs
+	const uint32_t unit = g * gridDim.x + blockIdx.x;
+	const bool unit_on = unit < T.units;
+	uint8_t* smem = smem_all + g * kSmemTotal;
+
 	if (decode_on)
 	{
-		if (threadIdx.x == 0)
+		if (role == 0 && utid == 0)
 		{
 			uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
 			for (uint32_t k = 0; k < kSlots; ++k)
@@ -58,16 +74,18 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) decode_kernel(DevTabl
 		}
 		__syncthreads();
 	}
+	if (!unit_on)
+		return;
 
-	if (threadIdx.x < kDecodeThreads)
+	if (role == 0)
 	{
 		if (decode_on)
-			decoder_main(T, smem);
+			decoder_main(T, smem, unit, utid, 1u + g);
 	}
-	else if (threadIdx.x < kDecodeThreads + kProducerThreads)
+	else if (role == 1)
 	{
 		if (decode_on)
-			producer_main(T, smem);
+			producer_main(T, smem, unit);
 	}
 	else if (walk_on)
 	{
@@ -78,11 +96,11 @@ __global__ void __launch_bounds__(kCtaThreads, kCtasPerSm) decode_kernel(DevTabl
 	}
 
 	// the last role to finish re-arms the counters for the next launch (stream order makes this visible)
-	if (threadIdx.x == 0 || threadIdx.x == kDecodeThreads + kProducerThreads)
+	if (utid == 0 && role != 1)
 	{
 		__threadfence();
 		uint32_t finished = atomicAdd(T.counters + 2, 1u);
-		if (finished == 2 * gridDim.x - 1)
+		if (finished == 2 * T.units - 1)
 		{
 			T.counters[0] = 0;
 			T.counters[1] = 0;
@@ -159,15 +177,15 @@ __global__ void __launch_bounds__(256) filter_kernel(uint8_t* data, size_t count
 
 cudaError_t prepare_decode_kernel()
 {
-	cudaError_t err = cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+	cudaError_t err = cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCta);
 	if (err != cudaSuccess)
 		return err;
-	return cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+	return cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCta);
 }
 
 cudaError_t decode_occupancy(int* ctas_per_sm)
 {
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, decode_kernel<false>, kCtaThreads, kSmemTotal);
+	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, decode_kernel<false>, kCtaThreads, kSmemCta);
 }
 
 cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream)
@@ -175,9 +193,9 @@ cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream
 	if (T.n_streams == 0)
 		return cudaSuccess;
 	if (T.wide_walk)
-		decode_kernel<true><<<grid, kCtaThreads, kSmemTotal, stream>>>(T);
+		decode_kernel<true><<<grid, kCtaThreads, kSmemCta, stream>>>(T);
 	else
-		decode_kernel<false><<<grid, kCtaThreads, kSmemTotal, stream>>>(T);
+		decode_kernel<false><<<grid, kCtaThreads, kSmemCta, stream>>>(T);
 	return cudaGetLastError();
 }
 
