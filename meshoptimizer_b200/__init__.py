@@ -61,7 +61,8 @@ EXPORTS = [
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    # MOB200_LIB: a variant build of the same sources (tools/ab.sh, diagnostics only)
+    return os.environ.get("MOB200_LIB") or _build.LIB_PATH
 
 
 def lib() -> ctypes.CDLL:

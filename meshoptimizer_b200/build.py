@@ -40,6 +40,17 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Diagnostics: the same sources with extra -D switches -> lib/variants/<name>.so (tools/ab.sh)."""
+    out = os.path.join(LIB_DIR, "variants", name + ".so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if it is missing or older than its sources; returns its path."""
     if not force and not stale():

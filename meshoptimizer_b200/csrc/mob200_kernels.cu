@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 
 	if (decode_on)
 	{
+		if (role == 0 && utid >= 32 && utid < 48)
+			reinterpret_cast<uint32_t*>(smem + kSmemPatch)[utid - 32] = patch_selector(utid - 32);
 		if (role == 0 && utid == 0)
 		{
 			uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
@@ -77,6 +79,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 	if (!unit_on)
 		return;
 
+#ifdef MOB200_DEBUG_ENDS
+	const long long ends_t0 = clock64();
+#endif
 	if (role == 0)
 	{
 		if (decode_on)
@@ -87,14 +92,31 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 		if (decode_on)
 			producer_main(T, smem, unit);
 	}
-	else if (walk_on)
+	else if (walk_on && (g < 4 || T.n_streams > 4u * 32u * gridDim.x))
 	{
+		// (the fifth walker shares a scheduler with the first: it only runs when four per SM cannot take every
+		// stream in one round -- one walker per scheduler is 9% faster alone and 3% faster fused)
 		if (kWideWalk)
 			walker_main_wide(T, smem + kSmemWalker);
 		else
 			walker_main(T, smem + kSmemWalker);
 	}
 
+#ifdef MOB200_DEBUG_ENDS
+	// diagnostics: when did the roles finish (cycles since the start of the CTA): slots 13 walker sum, 14 decoder max, 15 walker max
+	if (utid == 0 && role != 1)
+	{
+		unsigned long long* dbg = reinterpret_cast<unsigned long long*>(T.counters + 16);
+		const unsigned long long dt = (unsigned long long)(clock64() - ends_t0);
+		if (role == 2)
+		{
+			atomicAdd(dbg + 13, dt);
+			atomicMax(dbg + 15, dt);
+		}
+		else
+			atomicMax(dbg + 14, dt);
+	}
+#endif
 	// the last role to finish re-arms the counters for the next launch (stream order makes this visible)
 	if (utid == 0 && role != 1)
 	{

@@ -18,10 +18,11 @@ namespace mob200
 {
 
 // A CTA (one per SM) is kUnitsPerCta independent decode UNITS; a unit is four decoder warps, a producer warp and a
-// walker warp with their own slice of shared memory.  The warps of one role are contiguous in the CTA, the latency-
-// critical roles last: the SM's issue arbiters prefer the warp with the highest hardware warp id, so walkers win
-// over producers and producers over decoders, and warp w sits on scheduler w % 4, so every scheduler gets the same
-// mix of roles (with 6-warp CTAs the walkers crowded on two of the four schedulers, behind the decoders).
+// walker warp with their own slice of shared memory.  The warps of one role are contiguous in the CTA: warp w sits
+// on scheduler w % 4, so every scheduler gets the same mix of roles (five decoders, one or two producers, one
+// walker).  With five 6-warp CTAs per SM the walkers crowded on two of the four schedulers; a unit's decoder warps
+// meet at a barrier every block, so the most loaded scheduler set the pace (measured: fused 1.85 -> 1.70 ms, the
+// order of the roles inside the CTA made no difference).
 constexpr int kDecodeThreads = 128;  // a unit's decoder warps decode one block at a time: (vertex_size/4) x (vertices/16, rounded up to a power of two) work items
 constexpr int kProducerThreads = 32; // a unit's producer warp stages its next blocks (TMA) and resolves their cross-block carry
 constexpr int kWalkerThreads = 32;   // a unit's walker warp walks 32 streams, one per lane (or one stream with all lanes)
