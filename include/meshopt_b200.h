@@ -1,7 +1,8 @@
 /*
  * meshopt_b200.h -- C ABI of the B200-native meshoptimizer vertex-buffer decode path.
  *
- * Two groups of entry points, both exported from meshoptimizer_b200/lib/libmeshopt_b200.so:
+ * Groups of entry points, all exported from meshoptimizer_b200/lib/libmeshopt_b200.so (1 and 2 are the hot
+ * path; 3 and 4 are its callers' side: the index streams and the glTF bufferView loop around it):
  *
  *  1. DROP-IN symbols: exactly the signatures of the reference C API for this path, so an
  *     application (or an FFI binding) that links meshoptimizer can link this library instead:
@@ -140,6 +141,88 @@ MESHOPTIMIZER_API int mob200_plan_timing_history(mob200_Plan* plan, int max_runs
  * count <= 16.
  * Synchronises the device.  Returns 0 or MOB200_ERR_*. */
 MESHOPTIMIZER_API int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset);
+
+/* ---- 3. index streams (the other two modes of a compressed glTF bufferView) ---------------------- */
+
+/* Drop-in symbols, reference src/meshoptimizer.h:344 (meshopt_decodeIndexBuffer, impl. src/indexcodec.cpp:384-576),
+ * :351 (meshopt_decodeIndexVersion, impl. :364-382) and :376 (meshopt_decodeIndexSequence, impl. :647-703).
+ * HOST pointers, synchronous; 0 / -1 / -2 / -3 as the reference, MOB200_ERR_* otherwise.  index_size is 2 or 4;
+ * index_count of a triangle list is a multiple of 3 (the reference asserts both; here MOB200_ERR_ARGUMENT). */
+MESHOPTIMIZER_API int meshopt_decodeIndexBuffer(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
+MESHOPTIMIZER_API int meshopt_decodeIndexVersion(const unsigned char* buffer, size_t buffer_size);
+MESHOPTIMIZER_API int meshopt_decodeIndexSequence(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
+
+enum mob200_IndexKind
+{
+	MOB200_INDEX_TRIANGLES = 0, /* meshopt_decodeIndexBuffer   (glTF mode "TRIANGLES") */
+	MOB200_INDEX_SEQUENCE = 1   /* meshopt_decodeIndexSequence (glTF mode "INDICES")   */
+};
+
+/* One independent index stream.  The formats are sequential state machines, so a batch is decoded with one
+ * thread per stream: throughput comes from the number of streams (meshes, meshlets), not from their length. */
+typedef struct mob200_IndexStream
+{
+	const unsigned char* src;
+	size_t src_size;
+	void* dst; /* index_count * index_size bytes, aligned to index_size */
+	size_t index_count;
+	size_t index_size;
+	int kind;   /* enum mob200_IndexKind */
+	int status; /* out: reference return code */
+} mob200_IndexStream;
+
+/* src/dst are device pointers; one kernel launch on cuda_stream; synchronises on it to fetch the codes into
+ * streams[i].status.  Returns the number of failed streams or MOB200_ERR_*. */
+MESHOPTIMIZER_API int mob200_decode_index_batch_device(mob200_Context* ctx, mob200_IndexStream* streams, size_t n, void* cuda_stream);
+/* Same with host pointers (one staging round trip for the batch).  Synchronous and thread-safe. */
+MESHOPTIMIZER_API int mob200_decode_index_batch_host(mob200_Context* ctx, mob200_IndexStream* streams, size_t n);
+
+/* ---- 4. glTF bufferView front-end (reference gltf/parsegltf.cpp:561-627, decompressMeshopt) ------ */
+
+enum mob200_GltfMode
+{
+	MOB200_GLTF_ATTRIBUTES = 0, /* -> meshopt_decodeVertexBuffer + filter */
+	MOB200_GLTF_TRIANGLES = 1,  /* -> meshopt_decodeIndexBuffer */
+	MOB200_GLTF_INDICES = 2     /* -> meshopt_decodeIndexSequence */
+};
+
+/* One bufferView that carries EXT_meshopt_compression / KHR_meshopt_compression (field names as written by
+ * gltf/write.cpp:739-790): the compressed bytes are src_size bytes at src_offset of buffers[src_buffer]; the
+ * decompressed view is dst_size = count * stride bytes at dst_offset of buffers[dst_buffer] (the buffer the
+ * view itself names: gltfpack's "fallback" buffer). */
+typedef struct mob200_GltfView
+{
+	size_t view; /* index in bufferViews[] */
+	int mode;    /* enum mob200_GltfMode */
+	int filter;  /* enum mob200_Filter */
+	size_t src_buffer, src_offset, src_size;
+	size_t count, stride;
+	size_t dst_buffer, dst_offset, dst_size;
+	int status; /* scan: 0 or MOB200_ERR_ARGUMENT (violates the extension's rules, extern/cgltf.h:1645-1667);
+	               decode: reference return code of the view's codec */
+} mob200_GltfView;
+
+typedef struct mob200_GltfInfo
+{
+	size_t json_offset, json_size; /* JSON text inside the input */
+	size_t bin_offset, bin_size;   /* BIN chunk of a .glb (the bytes of buffers[0]); 0, 0 for bare JSON */
+	size_t buffer_count;           /* length of buffers[] */
+	size_t view_count;             /* compressed views found (may exceed view_capacity: call again) */
+	size_t invalid_views;          /* of which rejected by the extension's rules */
+} mob200_GltfInfo;
+
+/* Find the compressed bufferViews of a .glb container or of bare .gltf JSON text.  Writes up to view_capacity
+ * views and up to buffer_capacity byteLength values of buffers[] (either array may be NULL).  Host only, no
+ * device work.  Returns 0, or MOB200_ERR_ARGUMENT for a malformed container / JSON. */
+MESHOPTIMIZER_API int mob200_gltf_scan(const void* data, size_t size, mob200_GltfView* views, size_t view_capacity, size_t* buffer_sizes, size_t buffer_capacity, mob200_GltfInfo* info);
+
+/* Decode all views in one batch per codec family.  buffers[i] / outputs[i]: where buffers[i] of the asset is
+ * loaded / where decompressed views that belong to buffers[i] go (NULL entries make the views that need them
+ * fail with MOB200_ERR_ARGUMENT); buffer_sizes (optional) bounds the source ranges.  Host pointers, synchronous.
+ * Returns the number of views whose status is non-zero, or MOB200_ERR_*. */
+MESHOPTIMIZER_API int mob200_gltf_decode_host(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs);
+/* Same with device pointers in buffers[] / outputs[]. */
+MESHOPTIMIZER_API int mob200_gltf_decode_device(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* device_buffers, const size_t* buffer_sizes, void* const* device_outputs, void* cuda_stream);
 
 #ifdef __cplusplus
 }

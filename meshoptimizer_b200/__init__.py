@@ -35,6 +35,45 @@ _FILTER_BY_NAME = {
 ERR_CUDA, ERR_ARGUMENT = -100, -101
 
 
+INDEX_TRIANGLES, INDEX_SEQUENCE = 0, 1
+GLTF_ATTRIBUTES, GLTF_TRIANGLES, GLTF_INDICES = 0, 1, 2
+
+
+class IndexStream(ctypes.Structure):
+    """mirror of ``mob200_IndexStream``"""
+    _fields_ = [
+        ("src", c_void_p),
+        ("src_size", c_size_t),
+        ("dst", c_void_p),
+        ("index_count", c_size_t),
+        ("index_size", c_size_t),
+        ("kind", c_int),
+        ("status", c_int),
+    ]
+
+
+class GltfView(ctypes.Structure):
+    """mirror of ``mob200_GltfView``"""
+    _fields_ = [
+        ("view", c_size_t),
+        ("mode", c_int),
+        ("filter", c_int),
+        ("src_buffer", c_size_t), ("src_offset", c_size_t), ("src_size", c_size_t),
+        ("count", c_size_t), ("stride", c_size_t),
+        ("dst_buffer", c_size_t), ("dst_offset", c_size_t), ("dst_size", c_size_t),
+        ("status", c_int),
+    ]
+
+
+class GltfInfo(ctypes.Structure):
+    """mirror of ``mob200_GltfInfo``"""
+    _fields_ = [
+        ("json_offset", c_size_t), ("json_size", c_size_t),
+        ("bin_offset", c_size_t), ("bin_size", c_size_t),
+        ("buffer_count", c_size_t), ("view_count", c_size_t), ("invalid_views", c_size_t),
+    ]
+
+
 class Stream(ctypes.Structure):
     """mirror of ``mob200_Stream``"""
     _fields_ = [
@@ -57,6 +96,9 @@ EXPORTS = [
     "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
     "mob200_decode_batch_host", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
     "mob200_plan_last_timing", "mob200_plan_timing_history", "mob200_plan_debug_counters",
+    "meshopt_decodeIndexBuffer", "meshopt_decodeIndexVersion", "meshopt_decodeIndexSequence",
+    "mob200_decode_index_batch_device", "mob200_decode_index_batch_host",
+    "mob200_gltf_scan", "mob200_gltf_decode_host", "mob200_gltf_decode_device",
 ]
 
 
@@ -111,6 +153,22 @@ def lib() -> ctypes.CDLL:
     L.mob200_context_sm_count.restype = c_int
     L.mob200_context_sm_count.argtypes = [c_void_p]
     L.mob200_version.restype = c_char_p
+    for name in ("meshopt_decodeIndexBuffer", "meshopt_decodeIndexSequence"):
+        f = getattr(L, name)
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+    L.meshopt_decodeIndexVersion.restype = c_int
+    L.meshopt_decodeIndexVersion.argtypes = [c_void_p, c_size_t]
+    L.mob200_decode_index_batch_device.restype = c_int
+    L.mob200_decode_index_batch_device.argtypes = [c_void_p, POINTER(IndexStream), c_size_t, c_void_p]
+    L.mob200_decode_index_batch_host.restype = c_int
+    L.mob200_decode_index_batch_host.argtypes = [c_void_p, POINTER(IndexStream), c_size_t]
+    L.mob200_gltf_scan.restype = c_int
+    L.mob200_gltf_scan.argtypes = [c_void_p, c_size_t, POINTER(GltfView), c_size_t, POINTER(c_size_t), c_size_t, POINTER(GltfInfo)]
+    L.mob200_gltf_decode_host.restype = c_int
+    L.mob200_gltf_decode_host.argtypes = [c_void_p, POINTER(GltfView), c_size_t, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p)]
+    L.mob200_gltf_decode_device.restype = c_int
+    L.mob200_gltf_decode_device.argtypes = [c_void_p, POINTER(GltfView), c_size_t, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), c_void_p]
     _LIB = L
     return L
 
@@ -344,3 +402,126 @@ def filter_device(filter, device_ptr: int, count: int, stride: int, cuda_stream:
 
 def version() -> str:
     return lib().mob200_version().decode()
+
+
+# ---------------------------------------------------------------------------------------------
+# index streams (reference src/meshoptimizer.h:344-376; JS wrapper js/meshopt_decoder.mjs decodeIndexBuffer /
+# decodeIndexSequence)
+# ---------------------------------------------------------------------------------------------
+
+def decode_index_version(source) -> int:
+    """``meshopt_decodeIndexVersion``: 0 or 1, -1 for an invalid header."""
+    src = _as_u8(source)
+    return int(lib().meshopt_decodeIndexVersion(src.ctypes.data if src.size else None, src.size))
+
+
+def _decode_index_rc(symbol: str, count: int, size: int, source):
+    if size not in (2, 4):
+        raise ValueError("index size must be 2 or 4")
+    src = _as_u8(source)
+    out = np.zeros(max(count, 1), dtype=np.uint16 if size == 2 else np.uint32)
+    rc = getattr(lib(), symbol)(out.ctypes.data, count, size, src.ctypes.data if src.size else None, src.size)
+    return int(rc), out[:count]
+
+
+def decode_index_buffer_rc(count: int, size: int, source):
+    """``meshopt_decodeIndexBuffer`` on host memory; returns (return code, indices)."""
+    if count % 3:
+        raise ValueError("index count of a triangle list must be a multiple of 3")
+    return _decode_index_rc("meshopt_decodeIndexBuffer", count, size, source)
+
+
+def decode_index_sequence_rc(count: int, size: int, source):
+    """``meshopt_decodeIndexSequence`` on host memory; returns (return code, indices)."""
+    return _decode_index_rc("meshopt_decodeIndexSequence", count, size, source)
+
+
+def decode_index_buffer(count: int, size: int, source) -> np.ndarray:
+    rc, out = decode_index_buffer_rc(count, size, source)
+    if rc != 0:
+        raise RuntimeError(f"Malformed buffer data: {rc}")
+    return out
+
+
+def decode_index_sequence(count: int, size: int, source) -> np.ndarray:
+    rc, out = decode_index_sequence_rc(count, size, source)
+    if rc != 0:
+        raise RuntimeError(f"Malformed buffer data: {rc}")
+    return out
+
+
+def decode_index_batch_host(items: Sequence[tuple], ctx: Optional[Context] = None):
+    """items: (source bytes, index_count, index_size, kind) -> (list of index arrays, list of return codes);
+    one kernel launch for the whole batch (``mob200_decode_index_batch_host``)."""
+    ctx = ctx or default_context()
+    n = len(items)
+    arr = (IndexStream * max(n, 1))()
+    keep, outs = [], []
+    for i, (src, count, size, kind) in enumerate(items):
+        s = _as_u8(src)
+        keep.append(s)
+        o = np.zeros(max(count, 1), dtype=np.uint16 if size == 2 else np.uint32)
+        outs.append(o)
+        arr[i].src = s.ctypes.data if s.size else None
+        arr[i].src_size = s.size
+        arr[i].dst = o.ctypes.data
+        arr[i].index_count = count
+        arr[i].index_size = size
+        arr[i].kind = kind
+    rc = lib().mob200_decode_index_batch_host(ctx.handle, arr, n)
+    if rc < 0:
+        raise RuntimeError(f"mob200_decode_index_batch_host failed ({rc})")
+    return [o[: it[1]] for o, it in zip(outs, items)], [arr[i].status for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------
+# glTF bufferView front-end (reference gltf/parsegltf.cpp:561-627)
+# ---------------------------------------------------------------------------------------------
+
+def gltf_scan(data):
+    """``mob200_gltf_scan``: (views ctypes array, buffer byteLengths, info) of a .glb / .gltf JSON blob."""
+    src = _as_u8(data)
+    info = GltfInfo()
+    rc = lib().mob200_gltf_scan(src.ctypes.data, src.size, None, 0, None, 0, ctypes.byref(info))
+    if rc != 0:
+        raise ValueError(f"not a glTF asset ({rc})")
+    views = (GltfView * max(1, info.view_count))()
+    sizes = (c_size_t * max(1, info.buffer_count))()
+    rc = lib().mob200_gltf_scan(src.ctypes.data, src.size, views, info.view_count, sizes, info.buffer_count, ctypes.byref(info))
+    assert rc == 0
+    return views, [int(sizes[i]) for i in range(info.buffer_count)], info
+
+
+def gltf_decode_host(data, external_buffers: Optional[dict] = None, ctx: Optional[Context] = None):
+    """Decompress every meshopt-compressed bufferView of a .glb in one batched device decode.
+    Returns (dict buffer index -> uint8 array with the decompressed views at their byteOffset, views, info).
+    buffers[0] is the BIN chunk of the .glb; other source buffers come from ``external_buffers``."""
+    ctx = ctx or default_context()
+    src = _as_u8(data)
+    views, sizes, info = gltf_scan(src)
+    n = info.view_count
+    nb = max(1, info.buffer_count)
+    sources = dict(external_buffers or {})
+    if info.bin_size:
+        sources.setdefault(0, src[info.bin_offset : info.bin_offset + info.bin_size])
+    bufs = (c_void_p * nb)()
+    lens = (c_size_t * nb)()
+    keep = []
+    for i in range(info.buffer_count):
+        b = sources.get(i)
+        if b is not None:
+            b = _as_u8(b)
+            keep.append(b)
+            bufs[i] = b.ctypes.data
+            lens[i] = b.size
+    outputs = {}
+    outs = (c_void_p * nb)()
+    for k in range(n):
+        d = views[k].dst_buffer
+        if d < info.buffer_count and d not in outputs:
+            outputs[d] = np.zeros(max(sizes[d], 1), dtype=np.uint8)
+            outs[d] = outputs[d].ctypes.data
+    rc = lib().mob200_gltf_decode_host(ctx.handle, views, n, bufs, lens, outs)
+    if rc < 0:
+        raise RuntimeError(f"mob200_gltf_decode_host failed ({rc})")
+    return outputs, views, info

@@ -110,11 +110,23 @@ __device__ __forceinline__ uint32_t tile_offset(uint32_t r, uint32_t vs)
 	return r * vs + (r >> 4) * kTilePad;
 }
 
+#ifdef MOB200_DEBUG_ENDS
+__device__ unsigned long long g_dbg_spins; // diagnostics: failed mbarrier polls of the decoder warps
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+#ifdef MOB200_DEBUG_ENDS
+	uint32_t spins = 0;
+	while (!mbar_try_wait(bar, parity))
+		++spins;
+	if (spins && (threadIdx.x & 31u) == 0)
+		atomicAdd(&g_dbg_spins, (unsigned long long)spins);
+#else
 	while (!mbar_try_wait(bar, parity))
 	{
 	}
+#endif
 }
 
 // same for waits that are expected to be long (the producer waiting for a slot: a block takes the decoders a

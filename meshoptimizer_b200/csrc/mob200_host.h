@@ -1,0 +1,102 @@
+// mob200_host.h -- host-side state shared by the C-ABI translation units (mob200_api.cu, mob200_index.cu):
+// the per-device context with its staging buffers, and small RAII-free buffer helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "../../include/meshopt_b200.h"
+
+#define CUDA_TRY(expr)                                                                                      \
+	do                                                                                                      \
+	{                                                                                                       \
+		cudaError_t err__ = (expr);                                                                         \
+		if (err__ != cudaSuccess)                                                                           \
+		{                                                                                                   \
+			fprintf(stderr, "meshopt_b200: %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+			return MOB200_ERR_CUDA;                                                                         \
+		}                                                                                                   \
+	} while (0)
+
+struct DeviceBuffer
+{
+	void* ptr = nullptr;
+	size_t size = 0;
+
+	int reserve(size_t bytes)
+	{
+		if (bytes <= size)
+			return 0;
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr;
+		size = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		CUDA_TRY(cudaMalloc(&ptr, want));
+		size = want;
+		return 0;
+	}
+	void release()
+	{
+		if (ptr)
+			cudaFree(ptr);
+		ptr = nullptr;
+		size = 0;
+	}
+};
+
+struct PinnedBuffer
+{
+	void* ptr = nullptr;
+	size_t size = 0;
+
+	int reserve(size_t bytes)
+	{
+		if (bytes <= size)
+			return 0;
+		if (ptr)
+			cudaFreeHost(ptr);
+		ptr = nullptr;
+		size = 0;
+		size_t want = bytes + bytes / 4 + 256;
+		CUDA_TRY(cudaHostAlloc(&ptr, want, cudaHostAllocDefault));
+		size = want;
+		return 0;
+	}
+	void release()
+	{
+		if (ptr)
+			cudaFreeHost(ptr);
+		ptr = nullptr;
+		size = 0;
+	}
+};
+
+struct mob200_Context
+{
+	int device = 0;
+	int sm_count = 0;
+	int decode_ctas_per_sm = 1;
+	uint32_t walker_lead = 0;      // see DevTables::walker_lead
+	int wide_walk_mode = 2;        // 0 / 1 force the walker form, 2 = choose by stream count (MOB200_WIDE_WALK)
+	cudaStream_t stream = nullptr; // used by the host-pointer entry points
+	std::mutex mu;                 // host-pointer entry points share the staging buffers below
+	DeviceBuffer d_in, d_out;
+	PinnedBuffer h_in, h_out;
+	// mob200_decode_batch_host: chunks in flight
+	static const int kHostSlots = 3;
+	cudaStream_t slot_stream[kHostSlots] = {};
+	cudaEvent_t slot_done[kHostSlots] = {};
+	DeviceBuffer slot_arena[kHostSlots];
+	PinnedBuffer slot_h_in[kHostSlots], slot_h_out[kHostSlots];
+	PinnedBuffer h_status;
+};
+
+static inline int set_device(const mob200_Context* ctx)
+{
+	CUDA_TRY(cudaSetDevice(ctx->device));
+	return 0;
+}

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 		}
 		else
 			atomicMax(dbg + 14, dt);
+		if (unit == 0 && role == 0)
+			dbg[12] = g_dbg_spins; // (cumulative; read it as a difference between runs)
 	}
 #endif
 	// the last role to finish re-arms the counters for the next launch (stream order makes this visible)

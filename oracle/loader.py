@@ -47,7 +47,7 @@ def build(force: bool = False) -> None:
 
 def _stale(so: str) -> bool:
     t = os.path.getmtime(so)
-    srcs = ["vertexcodec_oracle.c", "vertexfilter_oracle.c", "harness.cpp", "Makefile"]
+    srcs = ["vertexcodec_oracle.c", "vertexfilter_oracle.c", "indexcodec_oracle.c", "harness.cpp", "Makefile"]
     return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in srcs)
 
 
@@ -75,6 +75,15 @@ class _Lib:
             f.restype = None
             f.argtypes = [c_void_p, c_size_t, c_size_t]
             self._filters[name.lower()] = f
+        self._index = {}
+        for name in ("decodeIndexBuffer", "decodeIndexSequence"):
+            f = getattr(L, prefix + name)
+            f.restype = c_int
+            f.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+            self._index[name] = f
+        self._index_version = getattr(L, prefix + "decodeIndexVersion")
+        self._index_version.restype = c_int
+        self._index_version.argtypes = [c_void_p, c_size_t]
         L.harness_decode_mt.restype = c_double
         L.harness_decode_mt.argtypes = [POINTER(HarnessStream), c_size_t, c_int, c_int, POINTER(c_double)]
         L.harness_hw_threads.restype = c_int
@@ -92,6 +101,18 @@ class _Lib:
     def decode_vertex_version(self, data) -> int:
         src = _u8(data)
         return self._version(src.ctypes.data if src.size else None, src.size)
+
+    def decode_index(self, kind: str, index_count: int, index_size: int, data) -> tuple[int, np.ndarray]:
+        """kind: 'triangles' (decodeIndexBuffer) or 'sequence' (decodeIndexSequence)"""
+        src = _u8(data)
+        out = np.zeros(max(index_count * index_size, 4), dtype=np.uint8)
+        f = self._index["decodeIndexBuffer" if kind == "triangles" else "decodeIndexSequence"]
+        rc = f(out.ctypes.data, index_count, index_size, src.ctypes.data if src.size else None, src.size)
+        return rc, out[: index_count * index_size].view(np.uint16 if index_size == 2 else np.uint32)
+
+    def decode_index_version(self, data) -> int:
+        src = _u8(data)
+        return self._index_version(src.ctypes.data if src.size else None, src.size)
 
     def decode_filter(self, name: str, buf: np.ndarray, count: int, stride: int) -> np.ndarray:
         out = np.ascontiguousarray(buf).view(np.uint8).reshape(-1).copy()
@@ -159,6 +180,25 @@ class _Ref(_Lib):
             f = getattr(L, "meshopt_encodeFilter" + name)
             f.restype = None
             f.argtypes = [c_void_p, c_size_t, c_size_t, c_int, c_void_p] + extra
+
+    def encode_index(self, kind: str, indices, vertex_count: int, version: int = 1) -> np.ndarray:
+        """reference index encoders (input generation): kind 'triangles' or 'sequence'"""
+        L = self.lib
+        idx = np.ascontiguousarray(indices, dtype=np.uint32)
+        L.meshopt_encodeIndexVersion.argtypes = [c_int]
+        L.meshopt_encodeIndexVersion(version)
+        name = "meshopt_encodeIndexBuffer" if kind == "triangles" else "meshopt_encodeIndexSequence"
+        bound = getattr(L, name + "Bound")
+        bound.restype = c_size_t
+        bound.argtypes = [c_size_t, c_size_t]
+        enc = getattr(L, name)
+        enc.restype = c_size_t
+        enc.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t]
+        buf = np.empty(int(bound(idx.size, vertex_count)), dtype=np.uint8)
+        n = enc(buf.ctypes.data, buf.size, idx.ctypes.data if idx.size else None, idx.size)
+        L.meshopt_encodeIndexVersion(1)
+        assert n > 0
+        return buf[:n].copy()
 
     def encode_bound(self, vertex_count: int, vertex_size: int) -> int:
         return int(self.lib.meshopt_encodeVertexBufferBound(vertex_count, vertex_size))
