@@ -38,7 +38,11 @@ extern "C"
 	size_t meshopt_encodeVertexBufferBound(size_t vertex_count, size_t vertex_size);
 	void meshopt_optimizeVertexCache(unsigned int* destination, const unsigned int* indices, size_t index_count, size_t vertex_count);
 	size_t meshopt_optimizeVertexFetch(void* destination, unsigned int* indices, size_t index_count, const void* vertices, size_t vertex_count, size_t vertex_size);
+	int meshopt_decodeIndexBuffer(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
+	int meshopt_decodeIndexSequence(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
 #define DECODE meshopt_decodeVertexBuffer
+#define DECODE_TRI meshopt_decodeIndexBuffer
+#define DECODE_SEQ meshopt_decodeIndexSequence
 #define F_OCT meshopt_decodeFilterOct
 #define F_QUAT meshopt_decodeFilterQuat
 #define F_EXP meshopt_decodeFilterExp
@@ -49,7 +53,11 @@ extern "C"
 	void oracle_decodeFilterQuat(void* buffer, size_t count, size_t stride);
 	void oracle_decodeFilterExp(void* buffer, size_t count, size_t stride);
 	void oracle_decodeFilterColor(void* buffer, size_t count, size_t stride);
+	int oracle_decodeIndexBuffer(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
+	int oracle_decodeIndexSequence(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
 #define DECODE oracle_decodeVertexBuffer
+#define DECODE_TRI oracle_decodeIndexBuffer
+#define DECODE_SEQ oracle_decodeIndexSequence
 #define F_OCT oracle_decodeFilterOct
 #define F_QUAT oracle_decodeFilterQuat
 #define F_EXP oracle_decodeFilterExp
@@ -65,12 +73,18 @@ struct HarnessStream
 	void* dst;
 	size_t vertex_count;
 	size_t vertex_size;
-	int filter; /* 0 none, 1 oct, 2 quat, 3 exp, 4 color */
+	int filter; /* 0 none, 1 oct, 2 quat, 3 exp, 4 color; 16 / 17: an INDEX stream (triangle list / sequence),
+	               vertex_count = index count, vertex_size = index size */
 	int status; /* out: return code of the decode call */
 };
 
 static void decode_one(HarnessStream& s)
 {
+	if (s.filter >= 16)
+	{
+		s.status = s.filter == 16 ? DECODE_TRI(s.dst, s.vertex_count, s.vertex_size, s.src, s.src_size) : DECODE_SEQ(s.dst, s.vertex_count, s.vertex_size, s.src, s.src_size);
+		return;
+	}
 	s.status = DECODE(s.dst, s.vertex_count, s.vertex_size, s.src, s.src_size);
 	if (s.status != 0)
 		return;
