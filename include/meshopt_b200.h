@@ -177,6 +177,31 @@ MESHOPTIMIZER_API int mob200_decode_index_batch_device(mob200_Context* ctx, mob2
 /* Same with host pointers (one staging round trip for the batch).  Synchronous and thread-safe. */
 MESHOPTIMIZER_API int mob200_decode_index_batch_host(mob200_Context* ctx, mob200_IndexStream* streams, size_t n);
 
+/* ---- 3b. meshlets (reference src/meshoptimizer.h:349-350; impl. src/meshletcodec.cpp:981-1051) --------- */
+
+/* Drop-in symbols: HOST pointers, synchronous; 0 / -2 / -3 as the reference.  vertex_count, triangle_count <= 256,
+ * vertex_size 2 or 4, triangle_size 3 or 4 (the reference asserts these; here MOB200_ERR_ARGUMENT).  The raw form
+ * writes exactly vertex_count / triangle_count 32-bit elements (the reference may also write the padding elements). */
+MESHOPTIMIZER_API int meshopt_decodeMeshlet(void* vertices, size_t vertex_count, size_t vertex_size, void* triangles, size_t triangle_count, size_t triangle_size, const unsigned char* buffer, size_t buffer_size);
+MESHOPTIMIZER_API int meshopt_decodeMeshletRaw(unsigned int* vertices, size_t vertex_count, unsigned int* triangles, size_t triangle_count, const unsigned char* buffer, size_t buffer_size);
+
+/* One encoded meshlet; decoded by one GPU thread, so batches of many meshlets are the intended use. */
+typedef struct mob200_Meshlet
+{
+	const unsigned char* src;
+	size_t src_size;
+	void* vertices; /* vertex_count * vertex_size bytes, aligned to vertex_size */
+	size_t vertex_count;
+	size_t vertex_size;
+	void* triangles; /* triangle_count * triangle_size bytes (4-byte aligned when triangle_size is 4) */
+	size_t triangle_count;
+	size_t triangle_size;
+	int status; /* out: reference return code */
+} mob200_Meshlet;
+
+MESHOPTIMIZER_API int mob200_decode_meshlet_batch_device(mob200_Context* ctx, mob200_Meshlet* meshlets, size_t n, void* cuda_stream);
+MESHOPTIMIZER_API int mob200_decode_meshlet_batch_host(mob200_Context* ctx, mob200_Meshlet* meshlets, size_t n);
+
 /* ---- 4. glTF bufferView front-end (reference gltf/parsegltf.cpp:561-627, decompressMeshopt) ------ */
 
 enum mob200_GltfMode

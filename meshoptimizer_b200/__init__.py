@@ -52,6 +52,16 @@ class IndexStream(ctypes.Structure):
     ]
 
 
+class Meshlet(ctypes.Structure):
+    """mirror of ``mob200_Meshlet``"""
+    _fields_ = [
+        ("src", c_void_p), ("src_size", c_size_t),
+        ("vertices", c_void_p), ("vertex_count", c_size_t), ("vertex_size", c_size_t),
+        ("triangles", c_void_p), ("triangle_count", c_size_t), ("triangle_size", c_size_t),
+        ("status", c_int),
+    ]
+
+
 class GltfView(ctypes.Structure):
     """mirror of ``mob200_GltfView``"""
     _fields_ = [
@@ -99,6 +109,7 @@ EXPORTS = [
     "meshopt_decodeIndexBuffer", "meshopt_decodeIndexVersion", "meshopt_decodeIndexSequence",
     "mob200_decode_index_batch_device", "mob200_decode_index_batch_host",
     "mob200_gltf_scan", "mob200_gltf_decode_host", "mob200_gltf_decode_device",
+    "meshopt_decodeMeshlet", "meshopt_decodeMeshletRaw", "mob200_decode_meshlet_batch_device", "mob200_decode_meshlet_batch_host",
 ]
 
 
@@ -163,6 +174,14 @@ def lib() -> ctypes.CDLL:
     L.mob200_decode_index_batch_device.argtypes = [c_void_p, POINTER(IndexStream), c_size_t, c_void_p]
     L.mob200_decode_index_batch_host.restype = c_int
     L.mob200_decode_index_batch_host.argtypes = [c_void_p, POINTER(IndexStream), c_size_t]
+    L.meshopt_decodeMeshlet.restype = c_int
+    L.meshopt_decodeMeshlet.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+    L.meshopt_decodeMeshletRaw.restype = c_int
+    L.meshopt_decodeMeshletRaw.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t]
+    L.mob200_decode_meshlet_batch_device.restype = c_int
+    L.mob200_decode_meshlet_batch_device.argtypes = [c_void_p, POINTER(Meshlet), c_size_t, c_void_p]
+    L.mob200_decode_meshlet_batch_host.restype = c_int
+    L.mob200_decode_meshlet_batch_host.argtypes = [c_void_p, POINTER(Meshlet), c_size_t]
     L.mob200_gltf_scan.restype = c_int
     L.mob200_gltf_scan.argtypes = [c_void_p, c_size_t, POINTER(GltfView), c_size_t, POINTER(c_size_t), c_size_t, POINTER(GltfInfo)]
     L.mob200_gltf_decode_host.restype = c_int
@@ -472,6 +491,47 @@ def decode_index_batch_host(items: Sequence[tuple], ctx: Optional[Context] = Non
     if rc < 0:
         raise RuntimeError(f"mob200_decode_index_batch_host failed ({rc})")
     return [o[: it[1]] for o, it in zip(outs, items)], [arr[i].status for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------
+# meshlets (reference src/meshoptimizer.h:349-350)
+# ---------------------------------------------------------------------------------------------
+
+def _meshlet_outputs(vertex_count, vertex_size, triangle_count, triangle_size):
+    if vertex_size not in (2, 4) or triangle_size not in (3, 4) or vertex_count > 256 or triangle_count > 256:
+        raise ValueError("meshlet: counts <= 256, vertex_size 2|4, triangle_size 3|4")
+    v = np.zeros(max(vertex_count, 1), dtype=np.uint16 if vertex_size == 2 else np.uint32)
+    t = np.zeros((max(triangle_count, 1), 3), dtype=np.uint8) if triangle_size == 3 else np.zeros(max(triangle_count, 1), dtype=np.uint32)
+    return v, t
+
+
+def decode_meshlet_rc(vertex_count: int, vertex_size: int, triangle_count: int, triangle_size: int, source):
+    """``meshopt_decodeMeshlet`` on host memory -> (return code, vertex references, triangles (u8[n,3] or packed u32[n]))"""
+    v, t = _meshlet_outputs(vertex_count, vertex_size, triangle_count, triangle_size)
+    src = _as_u8(source)
+    rc = lib().meshopt_decodeMeshlet(v.ctypes.data, vertex_count, vertex_size, t.ctypes.data, triangle_count, triangle_size, src.ctypes.data if src.size else None, src.size)
+    return int(rc), v[:vertex_count], t[:triangle_count]
+
+
+def decode_meshlet_batch_host(items: Sequence[tuple], ctx: Optional[Context] = None):
+    """items: (source, vertex_count, vertex_size, triangle_count, triangle_size) -> (list of (vertices, triangles), codes);
+    one kernel launch for the whole batch (``mob200_decode_meshlet_batch_host``)."""
+    ctx = ctx or default_context()
+    n = len(items)
+    arr = (Meshlet * max(n, 1))()
+    keep, outs = [], []
+    for i, (src, vc, vs, tc, ts) in enumerate(items):
+        s = _as_u8(src)
+        v, t = _meshlet_outputs(vc, vs, tc, ts)
+        keep.append(s)
+        outs.append((v[:vc], t[:tc]))
+        arr[i].src, arr[i].src_size = (s.ctypes.data if s.size else None), s.size
+        arr[i].vertices, arr[i].vertex_count, arr[i].vertex_size = v.ctypes.data, vc, vs
+        arr[i].triangles, arr[i].triangle_count, arr[i].triangle_size = t.ctypes.data, tc, ts
+    rc = lib().mob200_decode_meshlet_batch_host(ctx.handle, arr, n)
+    if rc < 0:
+        raise RuntimeError(f"mob200_decode_meshlet_batch_host failed ({rc})")
+    return outs, [arr[i].status for i in range(n)]
 
 
 # ---------------------------------------------------------------------------------------------

@@ -40,6 +40,8 @@ extern "C"
 	size_t meshopt_optimizeVertexFetch(void* destination, unsigned int* indices, size_t index_count, const void* vertices, size_t vertex_count, size_t vertex_size);
 	int meshopt_decodeIndexBuffer(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
 	int meshopt_decodeIndexSequence(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
+	int meshopt_decodeMeshlet(void* vertices, size_t vertex_count, size_t vertex_size, void* triangles, size_t triangle_count, size_t triangle_size, const unsigned char* buffer, size_t buffer_size);
+#define DECODE_MESHLET meshopt_decodeMeshlet
 #define DECODE meshopt_decodeVertexBuffer
 #define DECODE_TRI meshopt_decodeIndexBuffer
 #define DECODE_SEQ meshopt_decodeIndexSequence
@@ -55,6 +57,8 @@ extern "C"
 	void oracle_decodeFilterColor(void* buffer, size_t count, size_t stride);
 	int oracle_decodeIndexBuffer(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
 	int oracle_decodeIndexSequence(void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size);
+	int oracle_decodeMeshlet(void* vertices, size_t vertex_count, size_t vertex_size, void* triangles, size_t triangle_count, size_t triangle_size, const unsigned char* buffer, size_t buffer_size);
+#define DECODE_MESHLET oracle_decodeMeshlet
 #define DECODE oracle_decodeVertexBuffer
 #define DECODE_TRI oracle_decodeIndexBuffer
 #define DECODE_SEQ oracle_decodeIndexSequence
@@ -136,6 +140,35 @@ HARNESS_API double harness_decode_mt(HarnessStream* streams, size_t n, int threa
 		double s = std::chrono::duration<double>(t1 - t0).count();
 		if (seconds_out)
 			seconds_out[p] = s;
+		if (s < best)
+			best = s;
+	}
+	return best;
+}
+
+/* meshlets: same pool, one decode call per meshlet */
+struct HarnessMeshlet
+{
+	const unsigned char* src;
+	size_t src_size;
+	void* vertices;
+	size_t vertex_count, vertex_size;
+	void* triangles;
+	size_t triangle_count, triangle_size;
+	int status;
+};
+
+HARNESS_API double harness_decode_meshlets_mt(HarnessMeshlet* m, size_t n, int threads, int passes)
+{
+	double best = 1e30;
+	for (int p = 0; p < passes; ++p)
+	{
+		auto t0 = std::chrono::steady_clock::now();
+		parallel_for(n, threads, [&](size_t i) {
+			m[i].status = DECODE_MESHLET(m[i].vertices, m[i].vertex_count, m[i].vertex_size, m[i].triangles, m[i].triangle_count, m[i].triangle_size, m[i].src, m[i].src_size);
+		});
+		auto t1 = std::chrono::steady_clock::now();
+		double s = std::chrono::duration<double>(t1 - t0).count();
 		if (s < best)
 			best = s;
 	}

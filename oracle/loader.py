@@ -25,6 +25,15 @@ FILTER_NONE, FILTER_OCT, FILTER_QUAT, FILTER_EXP, FILTER_COLOR = 0, 1, 2, 3, 4
 FILTER_NAMES = {"none": 0, "oct": 1, "quat": 2, "exp": 3, "color": 4}
 
 
+class HarnessMeshlet(ctypes.Structure):
+    _fields_ = [
+        ("src", c_void_p), ("src_size", c_size_t),
+        ("vertices", c_void_p), ("vertex_count", c_size_t), ("vertex_size", c_size_t),
+        ("triangles", c_void_p), ("triangle_count", c_size_t), ("triangle_size", c_size_t),
+        ("status", c_int),
+    ]
+
+
 class HarnessStream(ctypes.Structure):
     _fields_ = [
         ("src", c_void_p),
@@ -47,7 +56,7 @@ def build(force: bool = False) -> None:
 
 def _stale(so: str) -> bool:
     t = os.path.getmtime(so)
-    srcs = ["vertexcodec_oracle.c", "vertexfilter_oracle.c", "indexcodec_oracle.c", "harness.cpp", "Makefile"]
+    srcs = ["vertexcodec_oracle.c", "vertexfilter_oracle.c", "indexcodec_oracle.c", "meshletcodec_oracle.c", "harness.cpp", "Makefile"]
     return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in srcs)
 
 
@@ -84,6 +93,11 @@ class _Lib:
         self._index_version = getattr(L, prefix + "decodeIndexVersion")
         self._index_version.restype = c_int
         self._index_version.argtypes = [c_void_p, c_size_t]
+        self._meshlet = getattr(L, prefix + "decodeMeshlet")
+        self._meshlet.restype = c_int
+        self._meshlet.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+        L.harness_decode_meshlets_mt.restype = c_double
+        L.harness_decode_meshlets_mt.argtypes = [POINTER(HarnessMeshlet), c_size_t, c_int, c_int]
         L.harness_decode_mt.restype = c_double
         L.harness_decode_mt.argtypes = [POINTER(HarnessStream), c_size_t, c_int, c_int, POINTER(c_double)]
         L.harness_hw_threads.restype = c_int
@@ -109,6 +123,31 @@ class _Lib:
         f = self._index["decodeIndexBuffer" if kind == "triangles" else "decodeIndexSequence"]
         rc = f(out.ctypes.data, index_count, index_size, src.ctypes.data if src.size else None, src.size)
         return rc, out[: index_count * index_size].view(np.uint16 if index_size == 2 else np.uint32)
+
+    def decode_meshlet(self, vertex_count: int, vertex_size: int, triangle_count: int, triangle_size: int, data):
+        """-> (rc, vertex references u16|u32, triangles: u8[count, 3] or packed u32[count])"""
+        src = _u8(data)
+        v = np.zeros(max(vertex_count, 1) + 4, dtype=np.uint16 if vertex_size == 2 else np.uint32)
+        t = np.zeros(max(triangle_count, 1) * 4 + 16, dtype=np.uint8)
+        rc = self._meshlet(v.ctypes.data, vertex_count, vertex_size, t.ctypes.data, triangle_count, triangle_size, src.ctypes.data if src.size else None, src.size)
+        tri = t[: triangle_count * 3].reshape(-1, 3) if triangle_size == 3 else t[: triangle_count * 4].view(np.uint32)
+        return rc, v[:vertex_count], tri
+
+    def decode_meshlets_mt(self, items, threads: int, passes: int = 1):
+        """items: (src, vertex_count, vertex_size, triangle_count, triangle_size); returns best seconds, statuses"""
+        n = len(items)
+        arr = (HarnessMeshlet * n)()
+        keep = []
+        for i, (src, vc, vs, tc, ts) in enumerate(items):
+            s = _u8(src)
+            v = np.zeros(vc * vs + 16, np.uint8)
+            t = np.zeros(tc * ts + 16, np.uint8)
+            keep += [s, v, t]
+            arr[i].src, arr[i].src_size = s.ctypes.data, s.size
+            arr[i].vertices, arr[i].vertex_count, arr[i].vertex_size = v.ctypes.data, vc, vs
+            arr[i].triangles, arr[i].triangle_count, arr[i].triangle_size = t.ctypes.data, tc, ts
+        best = self.lib.harness_decode_meshlets_mt(arr, n, threads, passes)
+        return best, [arr[i].status for i in range(n)]
 
     def decode_index_version(self, data) -> int:
         src = _u8(data)
@@ -197,6 +236,20 @@ class _Ref(_Lib):
         buf = np.empty(int(bound(idx.size, vertex_count)), dtype=np.uint8)
         n = enc(buf.ctypes.data, buf.size, idx.ctypes.data if idx.size else None, idx.size)
         L.meshopt_encodeIndexVersion(1)
+        assert n > 0
+        return buf[:n].copy()
+
+    def encode_meshlet(self, vertices, triangles) -> np.ndarray:
+        """reference meshopt_encodeMeshlet: vertices u32[<=256], triangles u8[n, 3] of local indices"""
+        L = self.lib
+        v = np.ascontiguousarray(vertices, dtype=np.uint32)
+        t = np.ascontiguousarray(triangles, dtype=np.uint8).reshape(-1, 3)
+        L.meshopt_encodeMeshletBound.restype = c_size_t
+        L.meshopt_encodeMeshletBound.argtypes = [c_size_t, c_size_t]
+        L.meshopt_encodeMeshlet.restype = c_size_t
+        L.meshopt_encodeMeshlet.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t]
+        buf = np.empty(int(L.meshopt_encodeMeshletBound(256, 256)), dtype=np.uint8)
+        n = L.meshopt_encodeMeshlet(buf.ctypes.data, buf.size, v.ctypes.data if v.size else None, v.size, t.ctypes.data if t.size else None, t.shape[0])
         assert n > 0
         return buf[:n].copy()
 

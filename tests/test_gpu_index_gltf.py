@@ -158,3 +158,46 @@ def test_gltf_device_variant_and_bad_view(mb):
     views2[0].src_size -= 5
     rc = mb.lib().mob200_gltf_decode_device(mb.default_context().handle, views2, info.view_count, bufs, lens, outs, None)
     assert rc == 1 and views2[0].status in (-2, -3) and all(views2[i].status == 0 for i in range(1, info.view_count))
+
+
+# ---- meshlets ---------------------------------------------------------------------------------------
+
+def test_meshlet_batch_matches_checker(mb, checker):
+    """encoder-produced meshlets in all four output formats, plus truncated / corrupted ones, in ONE launch"""
+    from oracle import loader
+    from tests.meshlet_cases import corruptions as meshlet_corruptions, meshlets
+    if not loader.have_ref():
+        pytest.skip("the reference encoder (oracle/_ref) is needed to produce meshlets")
+    R = loader.ref()
+    items, want = [], []
+    for ci, (name, verts, tris) in enumerate(meshlets()):
+        enc = R.encode_meshlet(verts, tris)
+        for vs in (2, 4):
+            for ts in (3, 4):
+                for e in [enc] + list(meshlet_corruptions(enc, seed=ci, n_random=6)):
+                    items.append((e, verts.size, vs, tris.shape[0], ts))
+                    want.append(checker.decode_meshlet(verts.size, vs, tris.shape[0], ts, e))
+    outs, rcs = mb.decode_meshlet_batch_host(items)
+    bad = 0
+    for i, ((rc_w, v_w, t_w), rc, (v, t)) in enumerate(zip(want, rcs, outs)):
+        assert rc == rc_w, (i, rc, rc_w)
+        if rc == 0:
+            assert np.array_equal(v, v_w) and np.array_equal(t, t_w), i
+        bad += rc != 0
+    assert len(items) > 300 and bad > 20
+
+
+def test_meshlet_dropin(mb, checker):
+    from oracle import loader
+    from tests.meshlet_cases import meshlets
+    if not loader.have_ref():
+        pytest.skip("the reference encoder (oracle/_ref) is needed to produce meshlets")
+    name, verts, tris = next(iter(meshlets()))
+    enc = loader.ref().encode_meshlet(verts, tris)
+    rc, v, t = mb.decode_meshlet_rc(verts.size, 4, tris.shape[0], 3, enc)
+    rc_w, v_w, t_w = checker.decode_meshlet(verts.size, 4, tris.shape[0], 3, enc)
+    assert rc == rc_w == 0 and np.array_equal(v, v_w) and np.array_equal(t, t_w)
+    rc, _, _ = mb.decode_meshlet_rc(verts.size, 2, tris.shape[0], 4, enc[:10])
+    assert rc == checker.decode_meshlet(verts.size, 2, tris.shape[0], 4, enc[:10])[0] == -2
+    with pytest.raises(ValueError):
+        mb.decode_meshlet_rc(300, 4, 10, 3, enc)
