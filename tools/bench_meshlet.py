@@ -1,0 +1,62 @@
+"""Secondary measurement: meshlet decode on the device.  Reference-encoded meshlets (64 vertices / 124 triangles, the
+clusterizer's usual limits), decoded by ONE launch of the thread-per-meshlet kernel with device-resident buffers
+(CUDA events, best of N), next to the reference decoder on all host threads.  Outputs verified against the reference."""
+import ctypes, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import meshoptimizer_b200 as mb
+from oracle import loader
+from tests.meshlet_cases import _strip
+
+R = loader.ref()
+dev = torch.device("cuda:0")
+ctx = mb.default_context()
+n = 400_000
+vc, tc = 64, 124
+rng = np.random.default_rng(5)
+variants = []
+for k in range(16):
+    verts = (np.sort(rng.integers(0, 1 << 20, vc)) + k * 4096).astype(np.uint32)
+    tris = _strip(vc, tc) if k % 2 == 0 else np.roll(_strip(vc, tc), k, axis=0)
+    variants.append((R.encode_meshlet(verts, tris), verts, tris))
+pitch = (max(v[0].size for v in variants) + 15) & ~15
+blob = np.zeros(n * pitch + 16, np.uint8)
+for i in range(n):
+    e = variants[i % 16][0]
+    blob[i * pitch : i * pitch + e.size] = e
+d_src = torch.from_numpy(blob).to(dev)
+d_v = torch.zeros(n * vc, dtype=torch.int32, device=dev)
+d_t = torch.zeros(n * tc, dtype=torch.int32, device=dev)
+arr = (mb.Meshlet * n)()
+for i in range(n):
+    arr[i].src, arr[i].src_size = d_src.data_ptr() + i * pitch, variants[i % 16][0].size
+    arr[i].vertices, arr[i].vertex_count, arr[i].vertex_size = d_v.data_ptr() + 4 * i * vc, vc, 4
+    arr[i].triangles, arr[i].triangle_count, arr[i].triangle_size = d_t.data_ptr() + 4 * i * tc, tc, 4
+best = 1e9
+for it in range(6):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = mb.lib().mob200_decode_meshlet_batch_device(ctx.handle, arr, n, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    e1.record()
+    torch.cuda.synchronize()
+    assert rc == 0
+    if it:
+        best = min(best, e0.elapsed_time(e1))
+gv = d_v.cpu().numpy().view(np.uint32).reshape(n, vc)
+gt = d_t.cpu().numpy().view(np.uint32).reshape(n, tc)
+ok = True
+for k in range(16):
+    rc, v, t = R.decode_meshlet(vc, 4, tc, 4, variants[k][0])
+    ok = ok and rc == 0 and bool((gv[k::16] == v[None, :]).all()) and bool((gt[k::16] == t[None, :]).all())
+threads = R.hw_threads()
+items = [(variants[i % 16][0], vc, 4, tc, 4) for i in range(100_000)]
+cpu_s, st = R.decode_meshlets_mt(items, threads, 3)
+assert all(s == 0 for s in st)
+decoded = n * (vc + tc) * 4
+print(json.dumps({"workload": f"{n} meshlets of {vc} vertices / {tc} triangles, 32-bit outputs", "encoded_MB": sum(variants[i % 16][0].size for i in range(n)) / 1e6,
+                  "decoded_MB": decoded / 1e6, "best_ms_incl_descriptor_upload_and_status": best, "meshlets_per_second": n / (best * 1e-3),
+                  "triangles_per_second": n * tc / (best * 1e-3), "decoded_GBps": decoded / best / 1e6,
+                  "cpu_reference_meshlets_per_second": len(items) / cpu_s, "cpu_reference_decoded_GBps": len(items) * (vc + tc) * 4 / cpu_s / 1e9, "cpu_threads": threads,
+                  "parity_ok": ok}, indent=1))
