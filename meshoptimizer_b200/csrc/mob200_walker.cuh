@@ -131,7 +131,7 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 	if (L.issued < ci)
 		L.issued = ci; // chunks that were jumped over are never read
 	uint32_t safe = L.issued * kWalkChunkBytes; // everything requested so far has landed
-	const uint32_t want = min(ci + kWalkChunks, L.last);
+	const uint32_t want = min(ci + kWalkChunks, L.last); // (topping up only three chunks ahead: walk alone 14 % slower, fused unchanged)
 	const uint32_t fresh = on ? want - min(want, L.issued) : 0u; // 0..4 chunks to request
 	const uint32_t fmax = __reduce_max_sync(0xffffffffu, fresh);
 
