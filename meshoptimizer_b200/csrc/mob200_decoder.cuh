@@ -474,9 +474,9 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 					S.carry[q] = prefix;
 				}
 			}
+			// every lane releases its own carry words (the barrier counts the 32 producer lanes)
+			mbar_arrive(carry_bar + slot);
 			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(carry_bar + slot);
 			dbg_look += dbg_clock() - c2;
 		}
 	}

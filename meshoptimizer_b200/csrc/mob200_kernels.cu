@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 			for (uint32_t k = 0; k < kSlots; ++k)
 			{
 				mbar_init(bars + k, 1);                          // full: the producer's arrive.expect_tx
-				mbar_init(bars + kSlots + k, 1);                 // carry: the producer
+				mbar_init(bars + kSlots + k, kProducerThreads);  // carry: every lane of the producer warp
 				mbar_init(bars + 2 * kSlots + k, kDecodeThreads / 32); // empty: one arrival per decoder warp
 			}
 			mbar_init(bars + 3 * kSlots, kDecodeThreads / 32);   // tile_free: one arrival per decoder warp
