@@ -198,7 +198,6 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	// decode order: streams are walked in waves of grid*32 (one lane each); inside a wave the decoders
 	// take block b of every stream before block b+1 of any, which is the order the walkers produce them
 	std::vector<uint2> ticket_info(total_blocks);
-	std::vector<uint32_t> block_ticket(total_blocks);
 	{
 		const size_t wave = (size_t)plan->grid * 32;
 		size_t t = 0;
@@ -214,7 +213,6 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 				for (size_t i = 0; i < live; ++i)
 				{
 					ticket_info[t] = make_uint2((uint32_t)(w0 + i), b);
-					block_ticket[host[w0 + i].block_base + b] = (uint32_t)t;
 					++t;
 				}
 			}
@@ -228,8 +226,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	size_t off_progress = align_up(off_table + total_chan * 32, 256);
 	size_t off_look = align_up(off_progress + n * 8, 256);
 	size_t off_tinfo = align_up(off_look + (total_chan / 4) * 8, 256);
-	size_t off_bticket = align_up(off_tinfo + total_blocks * 8, 256);
-	size_t off_status = align_up(off_bticket + total_blocks * 4, 256);
+	size_t off_status = align_up(off_tinfo + total_blocks * 8, 256);
 	size_t off_counters = align_up(off_status + n * 4, 256);
 	size_t arena_bytes = off_counters + 256;
 
@@ -256,7 +253,6 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.progress = reinterpret_cast<unsigned long long*>(base + off_progress);
 	plan->T.lookback = reinterpret_cast<unsigned long long*>(base + off_look);
 	plan->T.ticket_info = reinterpret_cast<uint2*>(base + off_tinfo);
-	plan->T.block_ticket = reinterpret_cast<uint32_t*>(base + off_bticket);
 	plan->T.status = reinterpret_cast<int32_t*>(base + off_status);
 	plan->T.counters = reinterpret_cast<uint32_t*>(base + off_counters);
 	plan->T.n_streams = (uint32_t)n;
@@ -279,7 +275,6 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	if (total_blocks)
 	{
 		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
-		ok = ok && cudaMemcpyAsync(base + off_bticket, block_ticket.data(), total_blocks * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
 	}
 	if (!ext_arena)
 		ok = ok && cudaStreamSynchronize(st) == cudaSuccess;

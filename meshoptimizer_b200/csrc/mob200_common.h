@@ -79,7 +79,6 @@ struct DevTables
 	unsigned long long* progress; // [n_streams]: epoch << 32 | codec version << 31 | number of blocks walked (release/acquire)
 	unsigned long long* lookback; // per block, vertex_size/4 entries: (epoch << 2 | state) << 32 | value
 	const uint2* ticket_info;     // [total_blocks]: decode order -> (stream, block)
-	const uint32_t* block_ticket; // [total_blocks]: global block id -> position in the decode order
 	int32_t* status;              // [n_streams] in CALLER order: reference return code per stream
 	uint32_t* counters;           // [0] decode ticket, [1] walker stream ticket, [2] finished roles
 	uint32_t n_streams;
