@@ -86,7 +86,10 @@ struct WalkLane
 	uint32_t limit;     // rel_end rounded up to 16: bytes at or beyond it are never fetched
 	uint32_t vs, count, bv, nblocks, version;
 	int status;
-	uint32_t sbase;     // shared-space address of this lane's ring (512-byte aligned)
+	uint32_t sbase;     // shared-space address of this lane's ring (512-byte aligned) XOR the lane's swizzle (lane % 8) << 4:
+	                    // byte p of the ring lives at sbase ^ p.  The rings of a warp are 512 bytes apart, i.e. on the same
+	                    // banks; the swizzle moves the 16-byte pieces that the lanes of a quarter-warp copy with one cp.async
+	                    // instruction to eight different bank groups (4 shared-memory wavefronts per instruction instead of ~28)
 	uint32_t issued;    // chunks [0, issued) have been requested or skipped
 	uint32_t last;      // number of chunks of the stream
 	uint32_t safe_end;  // bytes below it are in the ring (landed) as of the latest refill point
@@ -144,19 +147,19 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 			{
 				const uint32_t c = L.issued + k;
 				const uint32_t b0 = c * kWalkChunkBytes;
-				const uint32_t dst = L.sbase + (c & (kWalkChunks - 1)) * kWalkChunkBytes;
+				const uint32_t dst = (c & (kWalkChunks - 1)) * kWalkChunkBytes;
 				const uint8_t* src = L.org + b0;
 				if (L.limit - b0 >= kWalkChunkBytes)
 				{
 #pragma unroll
 					for (uint32_t j = 0; j < kWalkChunkBytes; j += 16)
-						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j), "l"(src + j) : "memory");
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(L.sbase ^ (dst + j)), "l"(src + j) : "memory");
 				}
 				else
 				{
 					// last chunk of the stream: only the 16-byte pieces inside [src & ~15, (src + size + 15) & ~15) are read
 					for (uint32_t j = 0; b0 + j < L.limit; j += 16)
-						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + j), "l"(src + j) : "memory");
+						asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(L.sbase ^ (dst + j)), "l"(src + j) : "memory");
 				}
 			}
 		}
@@ -188,7 +191,7 @@ __device__ __forceinline__ void walk_refill(WalkLane& L, WalkWarp& W, bool on, u
 __device__ __forceinline__ uint32_t ring_word(const WalkLane& L, uint32_t rel)
 {
 	uint32_t v;
-	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(L.sbase | (rel & (kWalkRingBytes - 4))));
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(L.sbase ^ (rel & (kWalkRingBytes - 4))));
 	return v;
 }
 
@@ -415,7 +418,7 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 	L.rel = L.rel0 + 1;
 	L.rel_end = L.rel0 + size;
 	L.limit = (L.rel_end + 15u) & ~15u;
-	L.sbase = ring_smem;
+	L.sbase = ring_smem | ((lane & 7u) << 4);
 	L.issued = 0;
 	L.safe_end = 0;
 	L.prefetched = 0;
