@@ -1,0 +1,24 @@
+"""Diagnostics: many short streams with small vertex sizes (gltfpack-style strides 4 / 8 / 12 / 16), device-resident."""
+import json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import meshoptimizer_b200 as mb
+from oracle import loader, workloads
+from tests.gpu_util import device_run
+
+res = []
+for kind, seg in (("oct8", 1024), ("quat12", 1024), ("exp15", 1024), ("oct8", 256), ("quat12", 256), ("exp15", 256)):
+    w = workloads.c3(kind, count=1 << 24, seg=seg, version=1, level=2)
+    outs, status, plan, guard = device_run(w, runs=8)
+    hist = plan.timing_history(8)
+    best = min(h["total_ms"] for h in hist[2:])
+    res.append({"workload": w.name, "segment": seg, "streams": w.n, "vertex_size": int(w.vertex_sizes[0]), "best_ms": best,
+                "decoded_GBps": w.decoded_bytes / best / 1e6, "traffic_GBps": (w.decoded_bytes + w.encoded_bytes) / best / 1e6, "ok": bool((status == 0).all() and guard)})
+    print(json.dumps(res[-1]), flush=True)
+v = loader.port().gen_js16(1 << 24)
+w = workloads.from_vertices("js16 16 Mi x 16B v1 L2, 4096-vertex streams", v, 16, 4096, 2, 1)
+outs, status, plan, guard = device_run(w, runs=8)
+best = min(h["total_ms"] for h in plan.timing_history(8)[2:])
+print(json.dumps({"workload": w.name, "streams": w.n, "vertex_size": 16, "best_ms": best, "decoded_GBps": w.decoded_bytes / best / 1e6, "ok": bool((status == 0).all() and np.array_equal(np.concatenate(outs), w.source))}))
