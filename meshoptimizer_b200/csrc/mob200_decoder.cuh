@@ -595,9 +595,292 @@ __device__ __forceinline__ uint4 unpack_group(
 	return r;
 }
 
+struct BlockRegs
+{
+	uint32_t vs, n, groups, gshift, items, stage_off, rows_off, filter, filter_kind, m_chunk;
+	bool first_block;
+	const uint16_t* rows_global;
+	uint8_t* out;
+	unsigned long long* lookback;
+};
+
+__device__ __forceinline__ BlockRegs load_block(const SlotData& S)
+{
+	const uint4 p0 = *reinterpret_cast<const uint4*>(&S.P.valid);
+	const uint4 p1 = *reinterpret_cast<const uint4*>(&S.P.gshift);
+	const uint4 p2 = *reinterpret_cast<const uint4*>(&S.P.first);
+	BlockRegs B;
+	B.vs = p0.y, B.n = p0.z, B.groups = p0.w;
+	B.gshift = p1.x, B.items = p1.y, B.stage_off = p1.z, B.rows_off = p1.w;
+	B.first_block = p2.x != 0, B.filter = p2.y, B.filter_kind = p2.z, B.m_chunk = p2.w;
+	B.rows_global = S.P.rows_global;
+	B.out = S.P.out;
+	B.lookback = S.P.lookback;
+	return B;
+}
+
+struct DecoderCtx
+{
+	uint8_t* ring;
+	uint8_t* tile;
+	const uint32_t* patch_lut;
+	uint64_t* tile_free;
+	unsigned long long tag;
+	uint32_t lane;
+};
+
+__device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotData& S, const BlockRegs& B, uint64_t* carry_slot, uint32_t phase,
+    uint32_t base, bool first_of_block, uint32_t tile_uses, long long& dbg_carry, long long& dbg_tile)
+{
+	uint8_t* ring = X.ring;
+	uint8_t* tile = X.tile;
+	const uint32_t* patch_lut = X.patch_lut;
+	uint64_t* tile_free = X.tile_free;
+	const unsigned long long tag = X.tag;
+	const uint32_t lane = X.lane;
+	const uint32_t vs = B.vs, groups = B.groups, gshift = B.gshift, items = B.items, stage_off = B.stage_off, rows_off = B.rows_off;
+	const bool first_block = B.first_block;
+	const uint16_t* rows_global = B.rows_global;
+	unsigned long long* lookback = B.lookback;
+	const uint32_t gstride = 1u << gshift;
+
+	const uint32_t item = base + lane;
+	const uint32_t q = item >> gshift;
+	const uint32_t c = item & (gstride - 1u);
+	const bool active = item < items && c < groups;
+
+	uint32_t w[16];
+	uint32_t total = 0;      // lane-wise sum of the 16 deltas
+	uint32_t channel = 0;
+	if (active)
+	{
+		channel = S.channels[q];
+
+		// this thread's four groups: byte-channels 4q..4q+3, group c
+		uint32_t e0, e1, e2, e3;
+		if (rows_off != kRowsInGlobal)
+		{
+			const uint16_t* rows = reinterpret_cast<const uint16_t*>(ring + rows_off) + (4 * q) * 16 + c;
+			e0 = rows[0], e1 = rows[16], e2 = rows[32], e3 = rows[48];
+		}
+		else
+		{
+			const uint16_t* rows = rows_global + (4 * q) * 16 + c;
+			e0 = __ldcg(rows), e1 = __ldcg(rows + 16), e2 = __ldcg(rows + 32), e3 = __ldcg(rows + 48);
+		}
+		uint4 pa = unpack_group(ring, stage_off, e0, patch_lut);
+		uint4 pb = unpack_group(ring, stage_off, e1, patch_lut);
+		uint4 pc = unpack_group(ring, stage_off, e2, patch_lut);
+		uint4 pd = unpack_group(ring, stage_off, e3, patch_lut);
+
+		const bool bytes = (channel & 3u) == 0;
+		if (bytes)
+		{
+			// byte deltas: un-zigzag in plane form, totals with dp4a (one add per four values)
+			pa.x = unzig8x4(pa.x), pa.y = unzig8x4(pa.y), pa.z = unzig8x4(pa.z), pa.w = unzig8x4(pa.w);
+			pb.x = unzig8x4(pb.x), pb.y = unzig8x4(pb.y), pb.z = unzig8x4(pb.z), pb.w = unzig8x4(pb.w);
+			pc.x = unzig8x4(pc.x), pc.y = unzig8x4(pc.y), pc.z = unzig8x4(pc.z), pc.w = unzig8x4(pc.w);
+			pd.x = unzig8x4(pd.x), pd.y = unzig8x4(pd.y), pd.z = unzig8x4(pd.z), pd.w = unzig8x4(pd.w);
+			const uint32_t ta = sum_bytes(pa), tb = sum_bytes(pb), tc = sum_bytes(pc), td = sum_bytes(pd);
+			total = __byte_perm(__byte_perm(ta, tb, 0x0040), __byte_perm(tc, td, 0x0040), 0x5410);
+		}
+
+		// 4 planes x 16 bytes -> 16 vertex words
+		const uint32_t A[4] = {pa.x, pa.y, pa.z, pa.w};
+		const uint32_t B[4] = {pb.x, pb.y, pb.z, pb.w};
+		const uint32_t C[4] = {pc.x, pc.y, pc.z, pc.w};
+		const uint32_t D[4] = {pd.x, pd.y, pd.z, pd.w};
+#pragma unroll
+		for (int j = 0; j < 4; ++j)
+		{
+			const uint32_t t0 = __byte_perm(A[j], B[j], 0x5140);
+			const uint32_t t1 = __byte_perm(A[j], B[j], 0x7362);
+			const uint32_t u0 = __byte_perm(C[j], D[j], 0x5140);
+			const uint32_t u1 = __byte_perm(C[j], D[j], 0x7362);
+			w[4 * j + 0] = __byte_perm(t0, u0, 0x5410);
+			w[4 * j + 1] = __byte_perm(t0, u0, 0x7632);
+			w[4 * j + 2] = __byte_perm(t1, u1, 0x5410);
+			w[4 * j + 3] = __byte_perm(t1, u1, 0x7632);
+		}
+
+		if (!bytes)
+		{
+			if ((channel & 3u) == 1)
+			{
+				// 16-bit deltas: un-zigzag per half word, totals with two-lane adds (VIADD.16x2)
+#pragma unroll
+				for (int j = 0; j < 16; ++j)
+					w[j] = ((w[j] >> 1) & 0x7fff7fffu) ^ ((w[j] & 0x00010001u) * 0xffffu);
+				total = w[0];
+#pragma unroll
+				for (int j = 1; j < 16; ++j)
+					total = __vadd2(total, w[j]);
+			}
+			else
+			{
+				// xor deltas: rotate right by the channel's amount
+				const uint32_t rot = (32u - (channel >> 4)) & 31u;
+#pragma unroll
+				for (int j = 0; j < 16; ++j)
+					w[j] = __funnelshift_l(w[j], w[j], rot);
+				total = w[0];
+#pragma unroll
+				for (int j = 1; j < 16; ++j)
+					total ^= w[j];
+			}
+		}
+	}
+	else
+	{
+#pragma unroll
+		for (int j = 0; j < 16; ++j)
+			w[j] = 0;
+	}
+	const uint32_t H = lane_mask(channel);
+
+	// scan of the chunk totals across the gstride threads of this lane q (inactive chunks add 0)
+	uint32_t incl = total;
+#pragma unroll
+	for (uint32_t dlt = 1; dlt < 16; dlt <<= 1)
+	{
+		const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dlt, 16); // (gstride divides 16: c >= dlt keeps the segments apart)
+		if (c >= dlt)
+			incl = lane_combine(o, incl, H);
+	}
+	uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1, gstride);
+	if (c == 0)
+		excl = 0;
+
+	// (block 0 publishes its inclusive prefix only: a look-back must never step below it)
+	const bool last = active && c == groups - 1;
+	if (last && !first_block)
+		st_volatile_u64(lookback + q, tag | (1ull << 32) | incl); // state 1: aggregate of this block
+
+	if (first_of_block)
+	{
+		const long long c0 = dbg_clock();
+		mbar_wait(carry_slot, phase);
+		const long long c1 = dbg_clock();
+		mbar_wait(tile_free, (tile_uses & 1u) ^ 1u); // every warp has finished storing the previous tile
+		dbg_carry += c1 - c0;
+		dbg_tile += dbg_clock() - c1;
+	}
+
+	if (active)
+	{
+		const uint32_t carry = S.carry[q];
+		if (last)
+			st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
+		uint32_t v = lane_combine(carry, excl, H);
+		uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
+		// one instruction stream for the three channel modes: a warp whose two lanes differ in mode does not run it twice
+#pragma unroll
+		for (int j = 0; j < 16; ++j)
+		{
+			v = lane_combine(v, w[j], H);
+			*reinterpret_cast<uint32_t*>(col) = v;
+			col += vs;
+		}
+	}
+}
+
+__device__ __forceinline__ void store_block(const BlockRegs& B, uint8_t* tile, uint32_t tid, uint32_t bar_id)
+{
+	const uint32_t vs = B.vs, n = B.n;
+	uint8_t* out = B.out;
+	const uint4 p2 = make_uint4(0u, B.filter, B.filter_kind, B.m_chunk);
+
+	// ---- tile -> global memory, decode filter on the way out ---------------------------------------------------------
+	{
+		const uint32_t nbytes = n * vs;
+		const uint32_t m_chunk = p2.w;
+		const int filter = (int)p2.y;
+		uint32_t fk = p2.z;
+		const uintptr_t oa = reinterpret_cast<uintptr_t>(out);
+		if (fk != 0 && (oa & 15) != 0)
+		{
+			// unaligned destination: filter inside the tile first (rare)
+			if (fk == 1)
+				for (uint32_t o = tid * 4; o < nbytes; o += kDecodeThreads * 4)
+				{
+					uint32_t* e = reinterpret_cast<uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+					*e = apply_filter32(*e, filter);
+				}
+			else
+				for (uint32_t r = tid; r < n; r += kDecodeThreads)
+				{
+					uint2* e = reinterpret_cast<uint2*>(tile + tile_offset(r, vs));
+					*e = apply_filter64(*e, filter);
+				}
+			decoder_sync(bar_id);
+			fk = 0;
+		}
+		if ((oa & 15) == 0)
+		{
+			const uint32_t pieces = nbytes >> 4;
+			if (fk == 0)
+			{
+#pragma unroll 4
+				for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
+				{
+					const uint32_t o = j << 4;
+					const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+					// (two 8-byte loads at a 16-byte lane stride are 2-way bank conflicts; a conflict-free lane order
+					// with four selects measured the same)
+					const uint2 lo = p[0], hi = p[1];
+					*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+				}
+			}
+			else
+			{
+				for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
+				{
+					const uint32_t o = j << 4;
+					const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+					uint2 lo = p[0], hi = p[1];
+					if (fk == 1)
+					{
+						lo.x = apply_filter32(lo.x, filter), lo.y = apply_filter32(lo.y, filter);
+						hi.x = apply_filter32(hi.x, filter), hi.y = apply_filter32(hi.y, filter);
+					}
+					else
+					{
+						lo = apply_filter64(lo, filter);
+						hi = apply_filter64(hi, filter);
+					}
+					*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+				}
+			}
+			const uint32_t rem_words = (nbytes & 15u) >> 2;
+			if (tid < rem_words)
+			{
+				const uint32_t o = (pieces << 4) + tid * 4;
+				const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+				if (fk == 2)
+				{
+					// one 8-byte element is left over (vs = 8, odd vertex count): thread 0 / 1 keep their half
+					const uint2 r = apply_filter64(*reinterpret_cast<const uint2*>(e - tid), filter);
+					*reinterpret_cast<uint32_t*>(out + o) = tid ? r.y : r.x;
+				}
+				else
+					*reinterpret_cast<uint32_t*>(out + o) = fk == 1 ? apply_filter32(*e, filter) : *e;
+			}
+		}
+		else if ((oa & 3) == 0)
+		{
+			for (uint32_t o = tid * 4; o < nbytes; o += kDecodeThreads * 4)
+				*reinterpret_cast<uint32_t*>(out + o) = *reinterpret_cast<const uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
+		}
+		else
+		{
+			for (uint32_t o = tid; o < nbytes; o += kDecodeThreads)
+				out[o] = tile[o + __umulhi(o, m_chunk) * kTilePad];
+		}
+	}
+}
+
 __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t unit, const uint32_t tid, const uint32_t bar_id)
 {
-	uint8_t* ring = smem + kSmemStage;
 	uint8_t* tile = smem + kSmemTile;
 	SlotData* slots = reinterpret_cast<SlotData*>(smem + kSmemSlots);
 	uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
@@ -607,7 +890,13 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 
 	const uint32_t lane = tid & 31u;
 	const uint32_t warp_base = tid & ~31u;
-	const uint32_t* patch_lut = reinterpret_cast<const uint32_t*>(smem + kSmemPatch);
+	DecoderCtx X;
+	X.ring = smem + kSmemStage;
+	X.tile = tile;
+	X.patch_lut = reinterpret_cast<const uint32_t*>(smem + kSmemPatch);
+	X.tile_free = tile_free;
+	X.tag = (unsigned long long)(T.epoch << 2) << 32;
+	X.lane = lane;
 	uint32_t tile_uses = 0;
 	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
 	const long long dbg_t0 = dbg_clock();
@@ -617,7 +906,6 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 		const uint32_t slot = i & (kSlots - 1);
 		const uint32_t phase = (i / kSlots) & 1u;
 		const SlotData& S = slots[slot];
-
 		{
 			const long long c0 = dbg_clock();
 			mbar_wait(full + slot, phase);
@@ -630,161 +918,9 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 				mbar_arrive(empty + slot);
 			continue;
 		}
-
-		const uint4 p0 = *reinterpret_cast<const uint4*>(&S.P.valid);     // valid vs n groups
-		const uint4 p1 = *reinterpret_cast<const uint4*>(&S.P.gshift);    // gshift items stage_off rows_off
-		const uint4 p2 = *reinterpret_cast<const uint4*>(&S.P.first);     // first filter filter_kind m_chunk
-		const uint32_t vs = p0.y, n = p0.z, groups = p0.w;
-		const uint32_t gshift = p1.x, items = p1.y, stage_off = p1.z, rows_off = p1.w;
-		const bool first_block = p2.x != 0;
-		const uint16_t* rows_global = S.P.rows_global;
-		uint8_t* out = S.P.out;
-		unsigned long long* lookback = S.P.lookback;
-		const uint32_t gstride = 1u << gshift;
-		const unsigned long long tag = (unsigned long long)(T.epoch << 2) << 32;
-
-		// ---- unpack + transpose + deltas + scans, all in registers; one pass per 128 work items ---------------------
-		for (uint32_t base = warp_base; base < items; base += kDecodeThreads)
-		{
-			const uint32_t item = base + lane;
-			const uint32_t q = item >> gshift;
-			const uint32_t c = item & (gstride - 1u);
-			const bool active = item < items && c < groups;
-
-			uint32_t w[16];
-			uint32_t total = 0;      // lane-wise sum of the 16 deltas
-			uint32_t channel = 0;
-			if (active)
-			{
-				channel = S.channels[q];
-
-				// this thread's four groups: byte-channels 4q..4q+3, group c
-				uint32_t e0, e1, e2, e3;
-				if (rows_off != kRowsInGlobal)
-				{
-					const uint16_t* rows = reinterpret_cast<const uint16_t*>(ring + rows_off) + (4 * q) * 16 + c;
-					e0 = rows[0], e1 = rows[16], e2 = rows[32], e3 = rows[48];
-				}
-				else
-				{
-					const uint16_t* rows = rows_global + (4 * q) * 16 + c;
-					e0 = __ldcg(rows), e1 = __ldcg(rows + 16), e2 = __ldcg(rows + 32), e3 = __ldcg(rows + 48);
-				}
-				uint4 pa = unpack_group(ring, stage_off, e0, patch_lut);
-				uint4 pb = unpack_group(ring, stage_off, e1, patch_lut);
-				uint4 pc = unpack_group(ring, stage_off, e2, patch_lut);
-				uint4 pd = unpack_group(ring, stage_off, e3, patch_lut);
-
-				const bool bytes = (channel & 3u) == 0;
-				if (bytes)
-				{
-					// byte deltas: un-zigzag in plane form, totals with dp4a (one add per four values)
-					pa.x = unzig8x4(pa.x), pa.y = unzig8x4(pa.y), pa.z = unzig8x4(pa.z), pa.w = unzig8x4(pa.w);
-					pb.x = unzig8x4(pb.x), pb.y = unzig8x4(pb.y), pb.z = unzig8x4(pb.z), pb.w = unzig8x4(pb.w);
-					pc.x = unzig8x4(pc.x), pc.y = unzig8x4(pc.y), pc.z = unzig8x4(pc.z), pc.w = unzig8x4(pc.w);
-					pd.x = unzig8x4(pd.x), pd.y = unzig8x4(pd.y), pd.z = unzig8x4(pd.z), pd.w = unzig8x4(pd.w);
-					const uint32_t ta = sum_bytes(pa), tb = sum_bytes(pb), tc = sum_bytes(pc), td = sum_bytes(pd);
-					total = __byte_perm(__byte_perm(ta, tb, 0x0040), __byte_perm(tc, td, 0x0040), 0x5410);
-				}
-
-				// 4 planes x 16 bytes -> 16 vertex words
-				const uint32_t A[4] = {pa.x, pa.y, pa.z, pa.w};
-				const uint32_t B[4] = {pb.x, pb.y, pb.z, pb.w};
-				const uint32_t C[4] = {pc.x, pc.y, pc.z, pc.w};
-				const uint32_t D[4] = {pd.x, pd.y, pd.z, pd.w};
-#pragma unroll
-				for (int j = 0; j < 4; ++j)
-				{
-					const uint32_t t0 = __byte_perm(A[j], B[j], 0x5140);
-					const uint32_t t1 = __byte_perm(A[j], B[j], 0x7362);
-					const uint32_t u0 = __byte_perm(C[j], D[j], 0x5140);
-					const uint32_t u1 = __byte_perm(C[j], D[j], 0x7362);
-					w[4 * j + 0] = __byte_perm(t0, u0, 0x5410);
-					w[4 * j + 1] = __byte_perm(t0, u0, 0x7632);
-					w[4 * j + 2] = __byte_perm(t1, u1, 0x5410);
-					w[4 * j + 3] = __byte_perm(t1, u1, 0x7632);
-				}
-
-				if (!bytes)
-				{
-					if ((channel & 3u) == 1)
-					{
-						// 16-bit deltas: un-zigzag per half word, totals with two-lane adds (VIADD.16x2)
-#pragma unroll
-						for (int j = 0; j < 16; ++j)
-							w[j] = ((w[j] >> 1) & 0x7fff7fffu) ^ ((w[j] & 0x00010001u) * 0xffffu);
-						total = w[0];
-#pragma unroll
-						for (int j = 1; j < 16; ++j)
-							total = __vadd2(total, w[j]);
-					}
-					else
-					{
-						// xor deltas: rotate right by the channel's amount
-						const uint32_t rot = (32u - (channel >> 4)) & 31u;
-#pragma unroll
-						for (int j = 0; j < 16; ++j)
-							w[j] = __funnelshift_l(w[j], w[j], rot);
-						total = w[0];
-#pragma unroll
-						for (int j = 1; j < 16; ++j)
-							total ^= w[j];
-					}
-				}
-			}
-			else
-			{
-#pragma unroll
-				for (int j = 0; j < 16; ++j)
-					w[j] = 0;
-			}
-			const uint32_t H = lane_mask(channel);
-
-			// scan of the chunk totals across the gstride threads of this lane q (inactive chunks add 0)
-			uint32_t incl = total;
-#pragma unroll
-			for (uint32_t dlt = 1; dlt < 16; dlt <<= 1)
-			{
-				const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dlt, 16); // (gstride divides 16: c >= dlt keeps the segments apart)
-				if (c >= dlt)
-					incl = lane_combine(o, incl, H);
-			}
-			uint32_t excl = __shfl_up_sync(0xffffffffu, incl, 1, gstride);
-			if (c == 0)
-				excl = 0;
-
-			// (block 0 publishes its inclusive prefix only: a look-back must never step below it)
-			const bool last = active && c == groups - 1;
-			if (last && !first_block)
-				st_volatile_u64(lookback + q, tag | (1ull << 32) | incl); // state 1: aggregate of this block
-
-			if (base == warp_base)
-			{
-				const long long c0 = dbg_clock();
-				mbar_wait(carry_bar + slot, phase);
-				const long long c1 = dbg_clock();
-				mbar_wait(tile_free, (tile_uses & 1u) ^ 1u); // every warp has finished storing the previous tile
-				dbg_carry += c1 - c0;
-				dbg_tile += dbg_clock() - c1;
-			}
-
-			if (active)
-			{
-				const uint32_t carry = S.carry[q];
-				if (last)
-					st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
-				uint32_t v = lane_combine(carry, excl, H);
-				uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
-				// one instruction stream for the three channel modes: a warp whose two lanes differ in mode does not run it twice
-#pragma unroll
-				for (int j = 0; j < 16; ++j)
-				{
-					v = lane_combine(v, w[j], H);
-					*reinterpret_cast<uint32_t*>(col) = v;
-					col += vs;
-				}
-			}
-		}
+		const BlockRegs B = load_block(S);
+		for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
+			decode_quantum(X, S, B, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
 		++tile_uses;
 
 		// this warp no longer needs the slot (staging bytes, rows, params, carry)
@@ -793,94 +929,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			mbar_arrive(empty + slot);
 
 		decoder_sync(bar_id); // the tile is complete
-
-		// ---- tile -> global memory, decode filter on the way out ---------------------------------------------------------
-		{
-			const uint32_t nbytes = n * vs;
-			const uint32_t m_chunk = p2.w;
-			const int filter = (int)p2.y;
-			uint32_t fk = p2.z;
-			const uintptr_t oa = reinterpret_cast<uintptr_t>(out);
-			if (fk != 0 && (oa & 15) != 0)
-			{
-				// unaligned destination: filter inside the tile first (rare)
-				if (fk == 1)
-					for (uint32_t o = tid * 4; o < nbytes; o += kDecodeThreads * 4)
-					{
-						uint32_t* e = reinterpret_cast<uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
-						*e = apply_filter32(*e, filter);
-					}
-				else
-					for (uint32_t r = tid; r < n; r += kDecodeThreads)
-					{
-						uint2* e = reinterpret_cast<uint2*>(tile + tile_offset(r, vs));
-						*e = apply_filter64(*e, filter);
-					}
-				decoder_sync(bar_id);
-				fk = 0;
-			}
-			if ((oa & 15) == 0)
-			{
-				const uint32_t pieces = nbytes >> 4;
-				if (fk == 0)
-				{
-#pragma unroll 4
-					for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
-					{
-						const uint32_t o = j << 4;
-						const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
-						// (two 8-byte loads at a 16-byte lane stride are 2-way bank conflicts; a conflict-free lane order
-						// with four selects measured the same)
-						const uint2 lo = p[0], hi = p[1];
-						*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-					}
-				}
-				else
-				{
-					for (uint32_t j = tid; j < pieces; j += kDecodeThreads)
-					{
-						const uint32_t o = j << 4;
-						const uint2* p = reinterpret_cast<const uint2*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
-						uint2 lo = p[0], hi = p[1];
-						if (fk == 1)
-						{
-							lo.x = apply_filter32(lo.x, filter), lo.y = apply_filter32(lo.y, filter);
-							hi.x = apply_filter32(hi.x, filter), hi.y = apply_filter32(hi.y, filter);
-						}
-						else
-						{
-							lo = apply_filter64(lo, filter);
-							hi = apply_filter64(hi, filter);
-						}
-						*reinterpret_cast<uint4*>(out + o) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-					}
-				}
-				const uint32_t rem_words = (nbytes & 15u) >> 2;
-				if (tid < rem_words)
-				{
-					const uint32_t o = (pieces << 4) + tid * 4;
-					const uint32_t* e = reinterpret_cast<const uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
-					if (fk == 2)
-					{
-						// one 8-byte element is left over (vs = 8, odd vertex count): thread 0 / 1 keep their half
-						const uint2 r = apply_filter64(*reinterpret_cast<const uint2*>(e - tid), filter);
-						*reinterpret_cast<uint32_t*>(out + o) = tid ? r.y : r.x;
-					}
-					else
-						*reinterpret_cast<uint32_t*>(out + o) = fk == 1 ? apply_filter32(*e, filter) : *e;
-				}
-			}
-			else if ((oa & 3) == 0)
-			{
-				for (uint32_t o = tid * 4; o < nbytes; o += kDecodeThreads * 4)
-					*reinterpret_cast<uint32_t*>(out + o) = *reinterpret_cast<const uint32_t*>(tile + o + __umulhi(o, m_chunk) * kTilePad);
-			}
-			else
-			{
-				for (uint32_t o = tid; o < nbytes; o += kDecodeThreads)
-					out[o] = tile[o + __umulhi(o, m_chunk) * kTilePad];
-			}
-		}
+		store_block(B, tile, tid, bar_id);
 		__syncwarp();
 		if (lane == 0)
 			mbar_arrive(tile_free);
