@@ -65,6 +65,8 @@ extern "C" int mob200_context_create(mob200_Context** out, int device)
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	if (const char* wide = getenv("MOB200_WIDE_WALK"))
 		ctx->wide_walk_mode = atoi(wide);
+	if (const char* rounds = getenv("MOB200_ROUNDS"))
+		ctx->rounds_mode = atoi(rounds);
 	if (const char* lead = getenv("MOB200_WALKER_LEAD"))
 		ctx->walker_lead = (uint32_t)strtoul(lead, nullptr, 10);
 	*out = ctx;
@@ -163,7 +165,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	});
 
 	std::vector<DevStream> host(n);
-	uint64_t total_blocks = 0, total_chan = 0;
+	uint64_t total_blocks = 0, total_chan = 0, small_blocks = 0; // small: a block of <= 16-byte vertices is at most two work quanta of the decoders
 	for (size_t i = 0; i < n; ++i)
 	{
 		const mob200_Stream& s = streams[order[i]];
@@ -180,6 +182,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 		d.block_groups = (uint8_t)(block_vertices((uint32_t)s.vertex_size) / kGroup);
 		d.caller_index = order[i];
 		total_blocks += d.nblocks;
+		small_blocks += s.vertex_size <= 16 ? d.nblocks : 0;
 		total_chan += (uint64_t)d.nblocks * s.vertex_size;
 		if (total_blocks >= 0xfffffff0ull)
 			return MOB200_ERR_ARGUMENT;
@@ -261,6 +264,8 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.epoch = 0;
 	plan->T.walker_lead = ctx->walker_lead;
 	// few streams: one walker WARP per stream (6x lower latency per block); many: one lane per stream
+	// mostly small-vertex blocks, and more blocks than units (a unit with one block has nothing to group): decode in rounds
+	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && total_blocks > plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
 	plan->T.wide_walk = ctx->wide_walk_mode == 2 ? (n < (size_t)2 * resident ? 1u : 0u) : (uint32_t)ctx->wide_walk_mode;
 
 	// table initialisation is enqueued on the context's stream and waited for, so that a later

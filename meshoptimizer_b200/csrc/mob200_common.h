@@ -87,6 +87,7 @@ struct DevTables
 	uint32_t epoch;               // changes every run, so progress / look-back entries never need clearing
 	uint32_t walker_lead;         // 0xffffffff = walk-only diagnostic mode (decoders off); otherwise unused
 	uint32_t wide_walk;           // 1: one warp per stream (few streams), 0: one lane per stream (many streams)
+	uint32_t rounds;              // 1: most blocks are small-vertex blocks (<= 16 bytes per vertex): decode them in rounds of up to four
 };
 
 } // namespace mob200

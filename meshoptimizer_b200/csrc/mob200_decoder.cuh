@@ -28,12 +28,11 @@
 namespace mob200
 {
 
-constexpr uint32_t kSlots = 4;                 // blocks in flight between producer and decoders
+constexpr uint32_t kRoundBlocks = 4;           // rounds variant: blocks the decoder warps of a unit take in one round (one warp per block)
 constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight
 constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
 constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
-constexpr uint32_t kTileBytes = kBlockBytes + 16 * kTilePad;
 
 struct BlockParams // written by the producer, read by the decoders after the slot's `full` barrier (80 bytes)
 {
@@ -52,7 +51,8 @@ struct BlockParams // written by the producer, read by the decoders after the sl
 	uint8_t* out;
 	const uint16_t* rows_global;
 	unsigned long long* lookback; // this block's entries (vs/4 of them); predecessors lie vs/4 entries lower each
-	unsigned long long pad;
+	uint32_t round_members;       // rounds variant: > 0: this block opens a decode round of so many consecutive blocks; 0: it continues one
+	uint32_t pad;
 };
 
 struct SlotData
@@ -63,26 +63,35 @@ struct SlotData
 	uint8_t channels[64];   // per 4-byte lane: channel byte (v1) or 0
 };
 
-// shared-memory map of one CTA (dynamic shared memory)
-constexpr uint32_t kSmemStage = 0;
-constexpr uint32_t kSmemTile = kSmemStage + kStageRingBytes;
-constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;                 // escape-byte selector table: 16 x 4 bytes
-constexpr uint32_t kSmemSlots = kSmemPatch + 64;
-constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
-constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;    // producer-private: ring_start[kSlots], ring_len[kSlots]
-constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
-constexpr uint32_t kSmemWalkerBytes = 32 * 512 + 6 * 4 * 32 + 16;                  // = kWalkSmemBytes (mob200_walker.cuh) >= kWideSmemBytes
-constexpr uint32_t kSmemTotal = (kSmemWalker + kSmemWalkerBytes + 1023) & ~1023u; // one unit
-constexpr uint32_t kSmemCta = kSmemTotal * kUnitsPerCta;
-static_assert(kSmemCta <= 227 * 1024, "shared memory of one CTA");
+// Shared-memory map of one unit (dynamic shared memory), for the two forms of the decode roles:
+//   kRounds = false  one block at a time goes round the four decoder warps (vertex sizes that fill them: > 16 bytes);
+//   kRounds = true   blocks of small vertices (one or two work quanta) are decoded up to four at a time, each in its
+//                    own part of the tile; eight blocks in flight between producer and decoders.
+template <bool kRounds>
+struct Lay
+{
+	static constexpr uint32_t kSlots = kRounds ? 8 : 4; // blocks in flight between producer and decoders
+	static constexpr uint32_t kTileBytes = kBlockBytes + (kRounds ? kRoundBlocks : 1) * 16 * kTilePad; // one 8 KB block, or up to four smaller ones side by side
+	static constexpr uint32_t kSmemStage = 0;
+	static constexpr uint32_t kSmemTile = kSmemStage + kStageRingBytes;
+	static constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;            // escape-byte selector table: 16 x 4 bytes
+	static constexpr uint32_t kSmemSlots = kSmemPatch + 64;
+	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
+	static constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;   // producer-private: ring_start[kSlots], ring_len[kSlots]
+	static constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
+	static constexpr uint32_t kSmemTotal = (kSmemWalker + 32 * 512 + 6 * 4 * 32 + 16 + 1023) & ~1023u; // one unit
+	static constexpr uint32_t kSmemCta = kSmemTotal * kUnitsPerCta;
+	static_assert(kSmemCta <= 227 * 1024, "shared memory of one CTA");
+	static_assert((kTileBytes & 15) == 0 && (kSmemTile & 15) == 0 && (kSmemPatch & 15) == 0 && (kSmemSlots & 15) == 0 && (kSmemBars & 7) == 0, "alignment");
+};
+constexpr uint32_t kSmemWalkerBytes = 32 * 512 + 6 * 4 * 32 + 16; // = kWalkSmemBytes (mob200_walker.cuh) >= kWideSmemBytes
 
 static_assert(sizeof(BlockParams) == 80 && sizeof(SlotData) == 416, "SlotData layout");
 static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs, "staging ring must hold the largest block");
-static_assert((kTileBytes & 15) == 0 && (kSmemTile & 15) == 0 && (kSmemPatch & 15) == 0 && (kSmemSlots & 15) == 0 && (kSmemBars & 7) == 0, "alignment");
 
 uint32_t decode_smem_bytes()
 {
-	return kSmemCta;
+	return Lay<true>::kSmemCta > Lay<false>::kSmemCta ? Lay<true>::kSmemCta : Lay<false>::kSmemCta;
 }
 
 __device__ __forceinline__ uint32_t magic_for(uint32_t d)
@@ -183,15 +192,18 @@ __device__ __forceinline__ unsigned long long* debug_counters(const DevTables& T
 	return reinterpret_cast<unsigned long long*>(T.counters + 16);
 }
 
+template <bool kRounds>
 __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t unit)
 {
+	using L = Lay<kRounds>;
+	constexpr uint32_t kSlots = L::kSlots;
 	const uint32_t lane = threadIdx.x & 31u;
-	uint8_t* ring = smem + kSmemStage;
-	SlotData* slots = reinterpret_cast<SlotData*>(smem + kSmemSlots);
-	uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+	uint8_t* ring = smem + L::kSmemStage;
+	SlotData* slots = reinterpret_cast<SlotData*>(smem + L::kSmemSlots);
+	uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kSmemBars);
 	uint64_t* carry_bar = full + kSlots;
 	uint64_t* empty = carry_bar + kSlots;
-	uint32_t* ring_start = reinterpret_cast<uint32_t*>(smem + kSmemProducer);
+	uint32_t* ring_start = reinterpret_cast<uint32_t*>(smem + L::kSmemProducer);
 	uint32_t* ring_len = ring_start + kSlots;
 
 	uint32_t head = 0;  // next free byte of the staging ring
@@ -211,6 +223,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		const uint32_t mi = i0 + lane;
 		const bool has = lane < kProducerBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0;
+		uint32_t m_quanta = 0, m_len = 0; // rounds variant: decoder work quanta (32 items each) and staged bytes of the block
 		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
 		const uint32_t* boff = nullptr;
 		const uint8_t* src = nullptr;
@@ -295,6 +308,13 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				m_lo = lo;
 				m_enc = (uint32_t)(hi - lo);
 				m_shift = (uint32_t)(a0 - lo);
+				if (kRounds)
+				{
+					const uint32_t groups_j = (m_n + kGroup - 1) / kGroup;
+					const uint32_t gshift_j = groups_j > 8 ? 4u : (groups_j > 4 ? 3u : (groups_j > 2 ? 2u : (groups_j > 1 ? 1u : 0u)));
+					m_quanta = (((vs >> 2) << gshift_j) + 31u) >> 5;
+					m_len = m_enc + (vs <= kRowsInRingMaxVs ? 32u * vs : 0u);
+				}
 			}
 		}
 		__syncwarp();
@@ -302,8 +322,40 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 
 		// ---- hand the blocks to the decoders, in order -------------------------------------------------------------
 		const uint32_t in_batch = min(kProducerBatch, my_count - i0);
-		for (uint32_t j = 0; j < in_batch; ++j)
+		// Rounds variant: the members of a round are all staged (slot, ring piece, TMA) before the carry of any of them is
+		// resolved -- the decoders start a round when every member has landed, and a carry may depend on a block that
+		// another unit decodes in a round of the same age, so a copy that waited for a carry could close a cycle.
+		uint32_t members = 1, g = 0, pass = 0;
+		for (uint32_t j0 = 0; j0 < in_batch;)
 		{
+			if (kRounds && pass == 0 && g == 0)
+			{
+				// a block of at most two work quanta is joined by the following blocks of this batch as long as the round
+				// stays within the four decoder warps and within half of the staging ring (all members are staged together)
+				uint32_t qs = __shfl_sync(0xffffffffu, m_quanta, j0);
+				members = 1;
+				if (qs <= 2)
+				{
+					uint32_t bs = __shfl_sync(0xffffffffu, m_len, j0);
+					bool open = true;
+#pragma unroll 1
+					for (uint32_t k = 1; k < kRoundBlocks && open && j0 + k < in_batch; ++k)
+					{
+						const uint32_t qn = __shfl_sync(0xffffffffu, m_quanta, (j0 + k) & 31u), bn = __shfl_sync(0xffffffffu, m_len, (j0 + k) & 31u);
+						if (qs + qn <= kDecodeThreads / 32 && bs + bn <= kStageRingBytes / 2)
+						{
+							qs += qn, bs += bn;
+							members = k + 1;
+							open = qs <= 2;
+						}
+						else
+							open = false;
+					}
+				}
+			}
+			const uint32_t j = j0 + g;
+			const uint32_t round_members = g == 0 ? members : 0u;
+			const bool do_stage = !kRounds || pass == 0, do_carry = !kRounds || pass == 1;
 			const uint32_t i = i0 + j;
 			const uint32_t slot = i & (kSlots - 1);
 			SlotData& S = slots[slot];
@@ -314,6 +366,8 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			const uint32_t b = __shfl_sync(0xffffffffu, m_b, j);
 			const uint8_t* tail = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, m_tail, j));
 
+			if (do_stage)
+			{
 			// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
 			const long long c1 = dbg_clock();
 			mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 400);
@@ -394,6 +448,8 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 					P.out = reinterpret_cast<uint8_t*>(m_out);
 					P.rows_global = reinterpret_cast<const uint16_t*>(m_rows);
 					P.lookback = reinterpret_cast<unsigned long long*>(m_look);
+					if (kRounds)
+						P.round_members = round_members;
 
 					fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
 					mbar_expect_tx(full + slot, len);
@@ -411,12 +467,18 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				{
 					ring_len[slot] = 0;
 					S.P.valid = 0;
+					if (kRounds)
+						S.P.round_members = round_members;
 					mbar_arrive(full + slot);
 				}
 				__syncwarp();
 			}
 
+			} // do_stage
+
 			// ---- carry into the block, per 4-byte lane ---------------------------------------------------------------
+			if (do_carry)
+			{
 			const long long c2 = dbg_clock();
 			bool carry_done = false;
 			if (valid && b > 0 && nq <= 8)
@@ -478,6 +540,17 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			mbar_arrive(carry_bar + slot);
 			__syncwarp();
 			dbg_look += dbg_clock() - c2;
+			} // do_carry
+
+			if (!kRounds)
+				++j0;
+			else if (++g == members)
+			{
+				g = 0;
+				if (pass == 1)
+					j0 += members;
+				pass ^= 1u;
+			}
 		}
 	}
 
@@ -619,21 +692,28 @@ __device__ __forceinline__ BlockRegs load_block(const SlotData& S)
 	return B;
 }
 
+// bytes of the output tile one block occupies: whole 16-vertex chunks (the last chunk is written in full even when
+// the block ends inside it) plus the per-chunk padding; a multiple of 16 because vs is a multiple of 4
+__device__ __forceinline__ uint32_t tile_span(uint32_t groups, uint32_t vs)
+{
+	return groups * (16u * vs + kTilePad) + ((groups & 1u) ? kTilePad : 0u);
+}
+
 struct DecoderCtx
 {
 	uint8_t* ring;
-	uint8_t* tile;
 	const uint32_t* patch_lut;
 	uint64_t* tile_free;
 	unsigned long long tag;
 	uint32_t lane;
 };
 
-__device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotData& S, const BlockRegs& B, uint64_t* carry_slot, uint32_t phase,
+// One work quantum: 32 items of one block (item = 4 byte-channels x 16 vertices): unpack, transposes, deltas and scans
+// in registers, finished words into the block's part of the output tile.
+__device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotData& S, const BlockRegs& B, uint8_t* tile, uint64_t* carry_slot, uint32_t phase,
     uint32_t base, bool first_of_block, uint32_t tile_uses, long long& dbg_carry, long long& dbg_tile)
 {
 	uint8_t* ring = X.ring;
-	uint8_t* tile = X.tile;
 	const uint32_t* patch_lut = X.patch_lut;
 	uint64_t* tile_free = X.tile_free;
 	const unsigned long long tag = X.tag;
@@ -879,11 +959,14 @@ __device__ __forceinline__ void store_block(const BlockRegs& B, uint8_t* tile, u
 	}
 }
 
+template <bool kRounds>
 __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t unit, const uint32_t tid, const uint32_t bar_id)
 {
-	uint8_t* tile = smem + kSmemTile;
-	SlotData* slots = reinterpret_cast<SlotData*>(smem + kSmemSlots);
-	uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+	using L = Lay<kRounds>;
+	constexpr uint32_t kSlots = L::kSlots;
+	uint8_t* tile = smem + L::kSmemTile;
+	SlotData* slots = reinterpret_cast<SlotData*>(smem + L::kSmemSlots);
+	uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kSmemBars);
 	uint64_t* carry_bar = full + kSlots;
 	uint64_t* empty = carry_bar + kSlots;
 	uint64_t* tile_free = empty + kSlots;
@@ -891,17 +974,22 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 	const uint32_t lane = tid & 31u;
 	const uint32_t warp_base = tid & ~31u;
 	DecoderCtx X;
-	X.ring = smem + kSmemStage;
-	X.tile = tile;
-	X.patch_lut = reinterpret_cast<const uint32_t*>(smem + kSmemPatch);
+	X.ring = smem + L::kSmemStage;
+	X.patch_lut = reinterpret_cast<const uint32_t*>(smem + L::kSmemPatch);
 	X.tile_free = tile_free;
 	X.tag = (unsigned long long)(T.epoch << 2) << 32;
 	X.lane = lane;
 	uint32_t tile_uses = 0;
 	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
 	const long long dbg_t0 = dbg_clock();
+	const uint32_t my_count = unit < T.total_blocks ? (T.total_blocks - unit + T.units - 1) / T.units : 0u;
 
-	for (uint32_t i = 0, t = unit; t < T.total_blocks; ++i, t += T.units)
+	// Rounds variant: one ROUND = consecutive blocks of this unit's sequence whose work fits the four decoder warps: a
+	// work quantum is 32 items (one warp), a block has ceil(items / 32) of them.  Blocks of small vertices (4 ... 16
+	// bytes: one or two quanta) share a round, each in its own part of the output tile, so that no decoder warp idles
+	// while its unit works on a block too small for four warps.  The producer decides the rounds
+	// (BlockParams::round_members of a round's first block).
+	for (uint32_t i = 0; i < my_count;)
 	{
 		const uint32_t slot = i & (kSlots - 1);
 		const uint32_t phase = (i / kSlots) & 1u;
@@ -911,28 +999,107 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			mbar_wait(full + slot, phase);
 			dbg_full += dbg_clock() - c0;
 		}
-		if (!S.P.valid)
+		const uint32_t members = kRounds ? S.P.round_members : 1u;
+
+		if (members <= 1)
 		{
+			// ---- one block: its quanta go round the four warps ---------------------------------------------------------
+			++i;
+			if (!S.P.valid)
+			{
+				__syncwarp();
+				if (lane == 0)
+					mbar_arrive(empty + slot);
+				continue;
+			}
+			const BlockRegs B = load_block(S);
+			for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
+				decode_quantum(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
+			++tile_uses;
+
+			// this warp no longer needs the slot (staging bytes, rows, params, carry)
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(empty + slot);
+
+			decoder_sync(bar_id); // the tile is complete
+			store_block(B, tile, tid, bar_id);
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(tile_free);
 			continue;
 		}
-		const BlockRegs B = load_block(S);
-		for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
-			decode_quantum(X, S, B, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
-		++tile_uses;
 
-		// this warp no longer needs the slot (staging bytes, rows, params, carry)
-		__syncwarp();
-		if (lane == 0)
-			mbar_arrive(empty + slot);
+		if (kRounds)
+		{
+			// ---- a round of several small blocks: one quantum per warp, every block in its own part of the tile ----------
+			uint32_t quanta = 0, tile_used = 0;
+			uint32_t mq[kRoundBlocks], moff[kRoundBlocks];
+#pragma unroll
+			for (uint32_t g = 0; g < kRoundBlocks; ++g)
+			{
+				mq[g] = 0, moff[g] = 0;
+				if (g < members)
+				{
+					const uint32_t sg = (i + g) & (kSlots - 1);
+					if (g > 0)
+					{
+						const long long c0 = dbg_clock();
+						mbar_wait(full + sg, ((i + g) / kSlots) & 1u);
+						dbg_full += dbg_clock() - c0;
+					}
+					const SlotData& Sg = slots[sg];
+					if (Sg.P.valid)
+					{
+						mq[g] = (Sg.P.items + 31u) >> 5;
+						moff[g] = tile_used;
+						tile_used += tile_span(Sg.P.groups, Sg.P.vs);
+						quanta += mq[g];
+					}
+				}
+			}
+			const uint32_t warp = tid >> 5;
+			if (warp < quanta)
+			{
+				// the member this warp's quantum belongs to
+				uint32_t g = 0, qb = 0;
+#pragma unroll
+				for (uint32_t h = 0; h + 1 < kRoundBlocks; ++h)
+					if (g == h && h + 1 < members && warp >= qb + mq[h])
+						qb += mq[h], g = h + 1;
+				uint8_t* btile = tile + (g == 0 ? moff[0] : (g == 1 ? moff[1] : (g == 2 ? moff[2] : moff[3])));
+				const uint32_t sg = (i + g) & (kSlots - 1);
+				const SlotData& Sg = slots[sg];
+				const BlockRegs B = load_block(Sg);
+				decode_quantum(X, Sg, B, btile, carry_bar + sg, ((i + g) / kSlots) & 1u, (warp - qb) * 32u, true, tile_uses, dbg_carry, dbg_tile);
+			}
+			++tile_uses;
 
-		decoder_sync(bar_id); // the tile is complete
-		store_block(B, tile, tid, bar_id);
-		__syncwarp();
-		if (lane == 0)
-			mbar_arrive(tile_free);
+			__syncwarp();
+			if (lane == 0)
+			{
+#pragma unroll
+				for (uint32_t g = 0; g < kRoundBlocks; ++g)
+					if (g < members)
+						mbar_arrive(empty + ((i + g) & (kSlots - 1)));
+			}
+
+			decoder_sync(bar_id); // the tiles of the round are complete
+
+#pragma unroll 1
+			for (uint32_t g = 0; g < members; ++g)
+			{
+				const SlotData& Sg = slots[(i + g) & (kSlots - 1)];
+				if (!Sg.P.valid)
+					continue;
+				const BlockRegs B = load_block(Sg);
+				store_block(B, tile + (g == 0 ? moff[0] : (g == 1 ? moff[1] : (g == 2 ? moff[2] : moff[3]))), tid, bar_id);
+			}
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(tile_free);
+			i += members;
+		}
 	}
 
 #ifdef MOB200_DEBUG_COUNTERS

@@ -81,6 +81,7 @@ struct mob200_Context
 	int sm_count = 0;
 	int decode_ctas_per_sm = 1;
 	uint32_t walker_lead = 0;      // see DevTables::walker_lead
+	int rounds_mode = 2;           // 0 / 1 force the decoder form, 2 = rounds when most blocks have <= 16-byte vertices (MOB200_ROUNDS)
 	int wide_walk_mode = 2;        // 0 / 1 force the walker form, 2 = choose by stream count (MOB200_WIDE_WALK)
 	cudaStream_t stream = nullptr; // used by the host-pointer entry points
 	std::mutex mu;                 // host-pointer entry points share the staging buffers below

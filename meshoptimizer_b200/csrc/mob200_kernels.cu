@@ -35,9 +35,14 @@ namespace mob200
 
 static_assert(kSmemWalkerBytes >= kWalkSmemBytes && kSmemWalkerBytes >= kWideSmemBytes, "walker shared-memory region");
 
-template <bool kWideWalk>
+// kWideWalk: one walker warp per stream (few streams) instead of one lane per stream.
+// kRounds:   blocks of small vertices (<= 16 bytes: one or two work quanta) are decoded up to four at a time by a unit's
+//            four decoder warps (Lay<true>); otherwise one block at a time goes round the four warps.
+template <bool kWideWalk, bool kRounds>
 __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 {
+	using L = Lay<kRounds>;
+	constexpr uint32_t kSlots = L::kSlots;
 	extern __shared__ __align__(1024) uint8_t smem_all[];
 
 	const bool decode_on = T.walker_lead != kWalkOnly;
@@ -56,15 +61,15 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 	// units than the device could hold still spreads over all SMs
 	const uint32_t unit = g * gridDim.x + blockIdx.x;
 	const bool unit_on = unit < T.units;
-	uint8_t* smem = smem_all + g * kSmemTotal;
+	uint8_t* smem = smem_all + g * L::kSmemTotal;
 
 	if (decode_on)
 	{
 		if (role == 0 && utid >= 32 && utid < 48)
-			reinterpret_cast<uint32_t*>(smem + kSmemPatch)[utid - 32] = patch_selector(utid - 32);
+			reinterpret_cast<uint32_t*>(smem + L::kSmemPatch)[utid - 32] = patch_selector(utid - 32);
 		if (role == 0 && utid == 0)
 		{
-			uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+			uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kSmemBars);
 			for (uint32_t k = 0; k < kSlots; ++k)
 			{
 				mbar_init(bars + k, 1);                          // full: the producer's arrive.expect_tx
@@ -85,21 +90,21 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 	if (role == 0)
 	{
 		if (decode_on)
-			decoder_main(T, smem, unit, utid, 1u + g);
+			decoder_main<kRounds>(T, smem, unit, utid, 1u + g);
 	}
 	else if (role == 1)
 	{
 		if (decode_on)
-			producer_main(T, smem, unit);
+			producer_main<kRounds>(T, smem, unit);
 	}
 	else if (walk_on && (g < 4 || T.n_streams > 4u * (kWideWalk ? 1u : 32u) * gridDim.x))
 	{
 		// (the fifth walker shares a scheduler with the first: it only runs when four per SM cannot take every
 		// stream in one round -- one walker per scheduler is 9% faster alone and 3% faster fused)
 		if (kWideWalk)
-			walker_main_wide(T, smem + kSmemWalker);
+			walker_main_wide(T, smem + L::kSmemWalker);
 		else
-			walker_main(T, smem + kSmemWalker);
+			walker_main(T, smem + L::kSmemWalker);
 	}
 
 #ifdef MOB200_DEBUG_ENDS
@@ -201,25 +206,44 @@ __global__ void __launch_bounds__(256) filter_kernel(uint8_t* data, size_t count
 
 cudaError_t prepare_decode_kernel()
 {
-	cudaError_t err = cudaFuncSetAttribute(decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCta);
-	if (err != cudaSuccess)
-		return err;
-	return cudaFuncSetAttribute(decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCta);
+	cudaError_t err = cudaFuncSetAttribute(decode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<false>::kSmemCta);
+	if (err == cudaSuccess)
+		err = cudaFuncSetAttribute(decode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<false>::kSmemCta);
+	if (err == cudaSuccess)
+		err = cudaFuncSetAttribute(decode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<true>::kSmemCta);
+	if (err == cudaSuccess)
+		err = cudaFuncSetAttribute(decode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<true>::kSmemCta);
+	return err;
 }
 
 cudaError_t decode_occupancy(int* ctas_per_sm)
 {
-	return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, decode_kernel<false>, kCtaThreads, kSmemCta);
+	int a = 0, b = 0;
+	cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, decode_kernel<false, false>, kCtaThreads, Lay<false>::kSmemCta);
+	if (err == cudaSuccess)
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, decode_kernel<false, true>, kCtaThreads, Lay<true>::kSmemCta);
+	*ctas_per_sm = a < b ? a : b;
+	return err;
 }
 
 cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream)
 {
 	if (T.n_streams == 0)
 		return cudaSuccess;
-	if (T.wide_walk)
-		decode_kernel<true><<<grid, kCtaThreads, kSmemCta, stream>>>(T);
+	if (T.rounds)
+	{
+		if (T.wide_walk)
+			decode_kernel<true, true><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
+		else
+			decode_kernel<false, true><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
+	}
 	else
-		decode_kernel<false><<<grid, kCtaThreads, kSmemCta, stream>>>(T);
+	{
+		if (T.wide_walk)
+			decode_kernel<true, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
+		else
+			decode_kernel<false, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
+	}
 	return cudaGetLastError();
 }
 

@@ -195,6 +195,23 @@ def c4(n_streams: int = 200_000, version: int = 1, level: int = 2) -> Workload:
                     np.zeros(n_streams, np.int32), source=None, meta={"level": level, "version": version})
 
 
+def merge(name: str, parts: List[Workload], interleave: bool = True) -> Workload:
+    """One batch out of several workloads (mixed vertex sizes / filters); interleave=True deals the streams round-robin."""
+    blobs, offs, cursor = [], [], 0
+    for w in parts:
+        pad = (-w.blob.size) % 16
+        blobs.append(np.concatenate([w.blob, np.zeros(pad, np.uint8)]))
+        offs.append(w.offsets + np.uint64(cursor))
+        cursor += w.blob.size + pad
+    cat = lambda f: np.concatenate([getattr(w, f) for w in parts])
+    offsets, sizes, counts, vss, filters = np.concatenate(offs), cat("sizes"), cat("counts"), cat("vertex_sizes"), cat("filters")
+    if interleave:
+        ids = np.concatenate([np.arange(w.n, dtype=np.float64) / max(w.n, 1) for w in parts])
+        order = np.argsort(ids, kind="stable")
+        offsets, sizes, counts, vss, filters = offsets[order], sizes[order], counts[order], vss[order], filters[order]
+    return Workload(name, np.concatenate(blobs), offsets, sizes, counts, vss, filters, source=None, meta={"parts": [w.name for w in parts]})
+
+
 def expected_outputs(w: Workload, lib=None, threads: int = 0) -> List[np.ndarray]:
     """Decode (and filter) every stream with a CPU checker (reference when available, else the port)."""
     lib = lib or (loader.ref() if loader.have_ref() else loader.port())

@@ -234,6 +234,46 @@ def test_c4_small_streams(mb, checker):
         assert np.array_equal(outs[i], want[i]), (i, int(w.counts[i]), int(w.vertex_sizes[i]), first_mismatch(outs[i], want[i]))
 
 
+# ---- small-vertex batches: the rounds form of the decode roles (up to four blocks per unit at a time) --------------------
+
+def _run_and_check(mb, w, checker, ctx=None, tag=""):
+    want = workloads.expected_outputs(w, lib=checker)
+    outs, status, _, guard = device_run(w, ctx=ctx, runs=2)
+    assert (status == 0).all() and guard, tag
+    names = {v: k for k, v in loader.FILTER_NAMES.items()}
+    for i in range(w.n):
+        _check_filtered(names.get(int(w.filters[i]), "none"), int(w.vertex_sizes[i]), outs[i], want[i], (tag, i))
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,count,seg", [
+    ("oct8", 800_000, None),      # one stream of 3125 four-byte blocks: every unit decodes rounds of four blocks of the SAME stream
+    ("quat12", 800_000, None),    # the same with 8-byte vertices
+    ("exp15", 900_000, None),     # 12-byte vertices: two quanta per block, rounds of two
+    ("color12", 2_560_000, 2560), # 1000 streams x 10 blocks: a block's predecessor sits one or two places earlier in another unit's queue
+    ("oct8", 1_000_000, 700),     # 1429 streams of three blocks (last one ragged)
+])
+def test_rounds_small_vertices(mb, checker, kind, count, seg):
+    w = workloads.c3(kind, count=count, seg=seg, version=1, level=2)
+    _run_and_check(mb, w, checker, tag=(kind, count, seg))
+
+
+@needs_ref
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_rounds_mixed_vertex_sizes(mb, checker, force, monkeypatch):
+    """4-, 8-, 12-, 16- and 32-byte vertices in one batch, filters on some, with either decoder form forced."""
+    parts = [workloads.c3("oct8", count=300_000, seg=1500), workloads.c3("quat12", count=200_000, seg=999),
+             workloads.c3("exp16", count=150_000, seg=4000), workloads.c1b(version=1, count=200_000),
+             workloads.c2(total=1 << 17, seg=3000, level=2, version=1), workloads.c3("color8", count=100_000, seg=257, version=0, level=0)]
+    w = workloads.merge("mixed", parts)
+    monkeypatch.setenv("MOB200_ROUNDS", force)
+    ctx = mb.Context(-1)
+    try:
+        _run_and_check(mb, w, checker, ctx=ctx, tag=("mixed", force))
+    finally:
+        ctx.close()
+
+
 @needs_ref
 def test_full_size_roundtrip_property(mb):
     """size-independent property at a large size: decode(encode(x)) == x for 16 Mi vertices (512 MB),
