@@ -165,7 +165,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	});
 
 	std::vector<DevStream> host(n);
-	uint64_t total_blocks = 0, total_chan = 0, small_blocks = 0; // small: a block of <= 16-byte vertices is at most two work quanta of the decoders
+	uint64_t total_blocks = 0, total_chan = 0, small_blocks = 0; // small: a block of <= 12-byte vertices (one or two work quanta of the decoders; 16-byte blocks gain nothing from rounds)
 	for (size_t i = 0; i < n; ++i)
 	{
 		const mob200_Stream& s = streams[order[i]];
@@ -182,7 +182,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 		d.block_groups = (uint8_t)(block_vertices((uint32_t)s.vertex_size) / kGroup);
 		d.caller_index = order[i];
 		total_blocks += d.nblocks;
-		small_blocks += s.vertex_size <= 16 ? d.nblocks : 0;
+		small_blocks += s.vertex_size <= 12 ? d.nblocks : 0;
 		total_chan += (uint64_t)d.nblocks * s.vertex_size;
 		if (total_blocks >= 0xfffffff0ull)
 			return MOB200_ERR_ARGUMENT;
@@ -264,8 +264,9 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.epoch = 0;
 	plan->T.walker_lead = ctx->walker_lead;
 	// few streams: one walker WARP per stream (6x lower latency per block); many: one lane per stream
-	// mostly small-vertex blocks, and more blocks than units (a unit with one block has nothing to group): decode in rounds
-	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && total_blocks > plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
+	// mostly small-vertex blocks and enough streams for the decoders to be the bottleneck (with fewer the walkers set the
+	// pace and a round only waits longer for its members: measured 5-15% slower at 1024 streams): decode in rounds
+	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && n >= (size_t)8 * plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
 	plan->T.wide_walk = ctx->wide_walk_mode == 2 ? (n < (size_t)2 * resident ? 1u : 0u) : (uint32_t)ctx->wide_walk_mode;
 
 	// table initialisation is enqueued on the context's stream and waited for, so that a later

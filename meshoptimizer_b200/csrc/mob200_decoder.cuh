@@ -1075,15 +1075,6 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			}
 			++tile_uses;
 
-			__syncwarp();
-			if (lane == 0)
-			{
-#pragma unroll
-				for (uint32_t g = 0; g < kRoundBlocks; ++g)
-					if (g < members)
-						mbar_arrive(empty + ((i + g) & (kSlots - 1)));
-			}
-
 			decoder_sync(bar_id); // the tiles of the round are complete
 
 #pragma unroll 1
@@ -1095,9 +1086,17 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 				const BlockRegs B = load_block(Sg);
 				store_block(B, tile + (g == 0 ? moff[0] : (g == 1 ? moff[1] : (g == 2 ? moff[2] : moff[3]))), tid, bar_id);
 			}
+			// the slots are released after the stores: the store parameters of the members are read from them (with eight
+			// slots the producer still stages the whole next round meanwhile)
 			__syncwarp();
 			if (lane == 0)
+			{
+#pragma unroll
+				for (uint32_t g = 0; g < kRoundBlocks; ++g)
+					if (g < members)
+						mbar_arrive(empty + ((i + g) & (kSlots - 1)));
 				mbar_arrive(tile_free);
+			}
 			i += members;
 		}
 	}

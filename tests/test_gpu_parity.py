@@ -236,13 +236,22 @@ def test_c4_small_streams(mb, checker):
 
 # ---- small-vertex batches: the rounds form of the decode roles (up to four blocks per unit at a time) --------------------
 
-def _run_and_check(mb, w, checker, ctx=None, tag=""):
+def _run_and_check(mb, w, checker, ctx=None, tag="", runs=2):
     want = workloads.expected_outputs(w, lib=checker)
-    outs, status, _, guard = device_run(w, ctx=ctx, runs=2)
+    outs, status, _, guard = device_run(w, ctx=ctx, runs=runs)
     assert (status == 0).all() and guard, tag
     names = {v: k for k, v in loader.FILTER_NAMES.items()}
     for i in range(w.n):
         _check_filtered(names.get(int(w.filters[i]), "none"), int(w.vertex_sizes[i]), outs[i], want[i], (tag, i))
+
+
+@pytest.fixture
+def rounds_ctx(mb, monkeypatch):
+    """a context with the rounds form forced on (the plan heuristic only picks it for many-stream batches)"""
+    monkeypatch.setenv("MOB200_ROUNDS", "1")
+    ctx = mb.Context(-1)
+    yield ctx
+    ctx.close()
 
 
 @needs_ref
@@ -252,10 +261,21 @@ def _run_and_check(mb, w, checker, ctx=None, tag=""):
     ("exp15", 900_000, None),     # 12-byte vertices: two quanta per block, rounds of two
     ("color12", 2_560_000, 2560), # 1000 streams x 10 blocks: a block's predecessor sits one or two places earlier in another unit's queue
     ("oct8", 1_000_000, 700),     # 1429 streams of three blocks (last one ragged)
+    ("oct8", 1 << 22, 1 << 12),   # 1024 streams x 16 blocks
+    ("exp16", 1 << 21, 1 << 11),  # 1024 streams x 8 blocks, 12-byte vertices
 ])
-def test_rounds_small_vertices(mb, checker, kind, count, seg):
+def test_rounds_small_vertices(mb, checker, rounds_ctx, kind, count, seg):
     w = workloads.c3(kind, count=count, seg=seg, version=1, level=2)
-    _run_and_check(mb, w, checker, tag=(kind, count, seg))
+    _run_and_check(mb, w, checker, ctx=rounds_ctx, tag=(kind, count, seg), runs=6)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,count,seg", [("oct8", 1 << 23, 256), ("quat12", 1 << 23, 512), ("exp15", 1 << 22, 300), ("color12", 1 << 22, 1024)])
+def test_rounds_many_streams(mb, checker, kind, count, seg):
+    """the regime the plan heuristic picks the rounds form for (decoders are the bottleneck, the producer runs ahead):
+    every byte compared"""
+    w = workloads.c3(kind, count=count, seg=seg, version=1, level=2)
+    _run_and_check(mb, w, checker, tag=(kind, count, seg), runs=6)
 
 
 @needs_ref

@@ -8,6 +8,16 @@ import meshoptimizer_b200 as mb
 from oracle import loader, workloads
 from tests.gpu_util import device_run
 
+def same(kind, stride, outs, want):
+    for a, b in zip(outs, want):
+        if stride == 4 and kind in ("oct8", "color8"):
+            d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+            if int(np.minimum(d, 256 - d).max()) > 1:
+                return False
+        elif not np.array_equal(a, b):
+            return False
+    return True
+
 res = []
 for kind, seg in (("oct8", 1024), ("quat12", 1024), ("exp15", 1024), ("oct8", 256), ("quat12", 256), ("exp15", 256)):
     w = workloads.c3(kind, count=1 << 24, seg=seg, version=1, level=2)
@@ -15,7 +25,7 @@ for kind, seg in (("oct8", 1024), ("quat12", 1024), ("exp15", 1024), ("oct8", 25
     hist = plan.timing_history(8)
     best = min(h["total_ms"] for h in hist[2:])
     res.append({"workload": w.name, "segment": seg, "streams": w.n, "vertex_size": int(w.vertex_sizes[0]), "best_ms": best,
-                "decoded_GBps": w.decoded_bytes / best / 1e6, "traffic_GBps": (w.decoded_bytes + w.encoded_bytes) / best / 1e6, "ok": bool((status == 0).all() and guard)})
+                "decoded_GBps": w.decoded_bytes / best / 1e6, "traffic_GBps": (w.decoded_bytes + w.encoded_bytes) / best / 1e6, "ok": bool((status == 0).all() and guard and same(kind, int(w.vertex_sizes[0]), outs, workloads.expected_outputs(w)))})
     print(json.dumps(res[-1]), flush=True)
 v = loader.port().gen_js16(1 << 24)
 w = workloads.from_vertices("js16 16 Mi x 16B v1 L2, 4096-vertex streams", v, 16, 4096, 2, 1)
