@@ -302,26 +302,31 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 						__syncwarp();
 					}
 
-					// the chain: one table lookup per group
+					// the chain: one table lookup per group.  The reference's 24-byte rule (:1385,:1415) is tested once, on the
+					// position of the last group: positions only grow, so it fails there if it fails anywhere, and the test
+					// (a branch on the running offset) stays out of the dependent chain  offset -> table byte -> offset.
+					// (Table indices stay below 16 + 16 * 24 whatever the bytes are; ring reads wrap inside the ring.)
 					uint32_t sel_bits = selectors;
+					uint32_t rel_last = rel;
+#pragma unroll 4
 					for (uint32_t g = 0; g < groups; ++g, sel_bits >>= 2)
 					{
-						if (rel_end - rel < kGroupReadLimit) // (:1385,:1415)
-						{
-							bad = true;
-							break;
-						}
 						const uint32_t sel = sel_bits & 3u;
 						const uint32_t idx = sel + (version ? ctrl : (uint32_t)(sel != 0u));
+						const uint32_t fixed = (1u << idx) & ~1u;
+						const uint32_t slot_base = tab_base + ((idx - 1u) & 3u) * 512u - win; // (idx 0 and 4 read a table byte they do not use)
+						rel_last = rel;
 						if (lane == g)
 							my_entry = idx ? (((rel - start) << 2) | (idx - 1u)) : 0u;
-						uint32_t cnt = 0;
-						if (idx >= 1 && idx <= 3)
-							asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cnt) : "r"(tab_base + (idx - 1u) * 512u + (rel - win)));
-						rel += ((1u << idx) & ~1u) + cnt;
+						uint32_t cnt;
+						asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cnt) : "r"(slot_base + rel));
+						rel += fixed + ((idx >= 1 && idx <= 3) ? cnt : 0u);
 					}
-					if (bad)
+					if (rel_end - rel_last < kGroupReadLimit || rel_last > rel_end)
+					{
+						bad = true;
 						break;
+					}
 				}
 
 				if (lane < 16 && (lane < 8 || groups > 8))
