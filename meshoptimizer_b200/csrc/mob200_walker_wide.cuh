@@ -10,8 +10,11 @@
 //      channel and computes, for each of its byte positions p and each field width w in {1,2,4} bits, the
 //      number of all-ones fields in the 2w bytes starting at p (SWAR per-byte counts, then sliding-window
 //      sums by doubling) -- i.e. the answer to "how many escape bytes would a w-bit group starting at p
-//      have" for EVERY p at once -- and stores the three 512-entry byte tables to shared memory;
-//   3. the chain then costs one shared-memory byte load and one add per group (uniform across the warp).
+//      have" for EVERY p at once -- and stores 2w + that count, the bytes such a group takes, to one of three
+//      512-entry byte tables in shared memory (two constant tables give 0 for a zero group and 16 for an
+//      8-bit group);
+//   3. the chain then costs one shared-memory byte load and one add per group (uniform across the warp);
+//      the 24-byte rule is tested once per channel, outside the chain.
 //
 // Outputs are identical to the lane-per-stream walker (mob200_walker.cuh): block byte ranges, one table row
 // of 16 group entries per byte-channel, a release store of the stream's progress per block, and the
@@ -26,7 +29,7 @@ namespace mob200
 constexpr uint32_t kWideChunk = 512;                 // bytes per cp.async chunk (32 lanes x 16 bytes)
 constexpr uint32_t kWideRingChunks = 4;
 constexpr uint32_t kWideRingBytes = kWideChunk * kWideRingChunks; // 2 KB
-constexpr uint32_t kWideTableBytes = 3 * 512;        // three window-count tables
+constexpr uint32_t kWideTableBytes = 5 * 512;        // per width index {0,1,2,4,8 bits}: bytes a group starting at window position p takes (0 and 16 are constants)
 constexpr uint32_t kWideSmemBytes = kWideRingBytes + kWideTableBytes;
 
 struct WideRing
@@ -281,7 +284,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 							for (int j = 0; j < 6; ++j)
 								n[j] = bytes_n4(w[j]);
 							window_sums<8>(n, out);
-							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + 1024 + lane * 16), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]) : "memory");
+							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + 1536 + lane * 16), "r"(out[0] + 0x08080808u), "r"(out[1] + 0x08080808u), "r"(out[2] + 0x08080808u), "r"(out[3] + 0x08080808u) : "memory");
 						}
 						if (used & 0x4u) // 2-bit fields: windows of 4 bytes
 						{
@@ -289,7 +292,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 							for (int j = 0; j < 6; ++j)
 								n[j] = bytes_n2(w[j]);
 							window_sums<4>(n, out);
-							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + 512 + lane * 16), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]) : "memory");
+							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + 1024 + lane * 16), "r"(out[0] + 0x04040404u), "r"(out[1] + 0x04040404u), "r"(out[2] + 0x04040404u), "r"(out[3] + 0x04040404u) : "memory");
 						}
 						if (used & 0x2u) // 1-bit fields: windows of 2 bytes
 						{
@@ -297,7 +300,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 							for (int j = 0; j < 6; ++j)
 								n[j] = bytes_n1(w[j]);
 							window_sums<2>(n, out);
-							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + lane * 16), "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3]) : "memory");
+							asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tab_base + 512 + lane * 16), "r"(out[0] + 0x02020202u), "r"(out[1] + 0x02020202u), "r"(out[2] + 0x02020202u), "r"(out[3] + 0x02020202u) : "memory");
 						}
 						__syncwarp();
 					}
@@ -313,14 +316,13 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 					{
 						const uint32_t sel = sel_bits & 3u;
 						const uint32_t idx = sel + (version ? ctrl : (uint32_t)(sel != 0u));
-						const uint32_t fixed = (1u << idx) & ~1u;
-						const uint32_t slot_base = tab_base + ((idx - 1u) & 3u) * 512u - win; // (idx 0 and 4 read a table byte they do not use)
+						const uint32_t slot_base = tab_base + idx * 512u - win; // table of this width: bytes a group at position p takes (fixed part + escape bytes)
 						rel_last = rel;
 						if (lane == g)
 							my_entry = idx ? (((rel - start) << 2) | (idx - 1u)) : 0u;
-						uint32_t cnt;
-						asm volatile("ld.shared.u8 %0, [%1];" : "=r"(cnt) : "r"(slot_base + rel));
-						rel += fixed + ((idx >= 1 && idx <= 3) ? cnt : 0u);
+						uint32_t step;
+						asm volatile("ld.shared.u8 %0, [%1];" : "=r"(step) : "r"(slot_base + rel));
+						rel += step;
 					}
 					if (rel_end - rel_last < kGroupReadLimit || rel_last > rel_end)
 					{
@@ -370,6 +372,10 @@ __device__ void walker_main_wide(const DevTables& T, uint8_t* smem_region)
 {
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t base = smem_addr(smem_region);
+	// the two constant step tables: a zero group takes no bytes, an 8-bit group 16 (the chain reads every step from a table)
+	asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + kWideRingBytes + lane * 16), "r"(0u) : "memory");
+	asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + kWideRingBytes + 2048 + lane * 16), "r"(0x10101010u) : "memory");
+	__syncwarp();
 	for (;;)
 	{
 		uint32_t s = 0;
