@@ -959,6 +959,23 @@ __device__ __forceinline__ void store_block(const BlockRegs& B, uint8_t* tile, u
 	}
 }
 
+// A decoder warp is done with a slot.  Plain form: the elected lane arrives for the warp (after __syncwarp: ordered
+// under the PTX memory model; one shared-memory atomic per warp and block).  Rounds form: every thread arrives for its
+// own reads -- the members' store parameters are read from the slots by all threads right before, and compute-
+// sanitizer's racecheck credits an arrival only to the arriving thread; per round the cost does not show.
+template <bool kRounds>
+__device__ __forceinline__ void release_slot(uint64_t* empty_bar, uint32_t lane)
+{
+	if (kRounds)
+		mbar_arrive(empty_bar);
+	else
+	{
+		__syncwarp();
+		if (lane == 0)
+			mbar_arrive(empty_bar);
+	}
+}
+
 template <bool kRounds>
 __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t unit, const uint32_t tid, const uint32_t bar_id)
 {
@@ -1007,9 +1024,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			++i;
 			if (!S.P.valid)
 			{
-				__syncwarp();
-				if (lane == 0)
-					mbar_arrive(empty + slot);
+				release_slot<kRounds>(empty + slot, lane);
 				continue;
 			}
 			const BlockRegs B = load_block(S);
@@ -1018,15 +1033,14 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			++tile_uses;
 
 			// this warp no longer needs the slot (staging bytes, rows, params, carry)
-			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(empty + slot);
+			release_slot<kRounds>(empty + slot, lane);
 
 			decoder_sync(bar_id); // the tile is complete
 			store_block(B, tile, tid, bar_id);
-			__syncwarp();
-			if (lane == 0)
-				mbar_arrive(tile_free);
+			// every thread arrives for its own reads of the tile (an elected lane's arrival after __syncwarp is just as
+			// ordered under the PTX memory model and measured the same, but compute-sanitizer's racecheck credits an
+			// arrival only to the arriving thread)
+			mbar_arrive(tile_free);
 			continue;
 		}
 
@@ -1088,15 +1102,11 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			}
 			// the slots are released after the stores: the store parameters of the members are read from them (with eight
 			// slots the producer still stages the whole next round meanwhile)
-			__syncwarp();
-			if (lane == 0)
-			{
 #pragma unroll
-				for (uint32_t g = 0; g < kRoundBlocks; ++g)
-					if (g < members)
-						mbar_arrive(empty + ((i + g) & (kSlots - 1)));
-				mbar_arrive(tile_free);
-			}
+			for (uint32_t g = 0; g < kRoundBlocks; ++g)
+				if (g < members)
+					release_slot<true>(empty + ((i + g) & (kSlots - 1)), lane);
+			mbar_arrive(tile_free);
 			i += members;
 		}
 	}

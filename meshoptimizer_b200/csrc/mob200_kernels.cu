@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 			{
 				mbar_init(bars + k, 1);                          // full: the producer's arrive.expect_tx
 				mbar_init(bars + kSlots + k, kProducerThreads);  // carry: every lane of the producer warp
-				mbar_init(bars + 2 * kSlots + k, kDecodeThreads / 32); // empty: one arrival per decoder warp
+				mbar_init(bars + 2 * kSlots + k, kRounds ? kDecodeThreads : kDecodeThreads / 32); // empty: one arrival per decoder warp (plain form) or thread (rounds form)
 			}
-			mbar_init(bars + 3 * kSlots, kDecodeThreads / 32);   // tile_free: one arrival per decoder warp
+			mbar_init(bars + 3 * kSlots, kDecodeThreads);        // tile_free: one arrival per decoder thread
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		__syncthreads();

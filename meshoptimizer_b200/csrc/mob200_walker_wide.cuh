@@ -309,19 +309,24 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 					// position of the last group: positions only grow, so it fails there if it fails anywhere, and the test
 					// (a branch on the running offset) stays out of the dependent chain  offset -> table byte -> offset.
 					// (Table indices stay below 16 + 16 * 24 whatever the bytes are; ring reads wrap inside the ring.)
+					// (Software-pipelined by hand: the table of group g+1 is worked out between the load of group g's step and
+					// its first use, so the chain is  add -> LDS -> add  and nothing else waits behind the load.)
 					uint32_t sel_bits = selectors;
 					uint32_t rel_last = rel;
+					uint32_t idx = (sel_bits & 3u) + (version ? ctrl : (uint32_t)((sel_bits & 3u) != 0u));
+					uint32_t slot_base = tab_base + idx * 512u - win; // table of this width: bytes a group at position p takes (fixed part + escape bytes)
 #pragma unroll 4
-					for (uint32_t g = 0; g < groups; ++g, sel_bits >>= 2)
+					for (uint32_t g = 0; g < groups; ++g)
 					{
-						const uint32_t sel = sel_bits & 3u;
-						const uint32_t idx = sel + (version ? ctrl : (uint32_t)(sel != 0u));
-						const uint32_t slot_base = tab_base + idx * 512u - win; // table of this width: bytes a group at position p takes (fixed part + escape bytes)
+						uint32_t step;
+						asm volatile("ld.shared.u8 %0, [%1];" : "=r"(step) : "r"(slot_base + rel));
 						rel_last = rel;
 						if (lane == g)
 							my_entry = idx ? (((rel - start) << 2) | (idx - 1u)) : 0u;
-						uint32_t step;
-						asm volatile("ld.shared.u8 %0, [%1];" : "=r"(step) : "r"(slot_base + rel));
+						sel_bits >>= 2;
+						idx = (sel_bits & 3u) + (version ? ctrl : (uint32_t)((sel_bits & 3u) != 0u));
+						slot_base = tab_base + idx * 512u - win;
+						asm volatile("" : "+r"(slot_base)); // (keeps idx * 512 out of the sum with the running offset)
 						rel += step;
 					}
 					if (rel_end - rel_last < kGroupReadLimit || rel_last > rel_end)
@@ -345,7 +350,9 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 			if (lane == 0)
 			{
 				boff[b + 1] = rel - rel0;
-				__threadfence(); // the table rows were written by other lanes: order them before the release below
+				// (the table rows were written by other lanes before the __syncwarp above: the release below is a
+				// fence + store and cumulative over what this lane has synchronised with, so no fence of its own is
+				// needed here -- a second MEMBAR.GPU per block was a fifth of the walk of a 4-byte-vertex stream)
 				st_release_u64(progress, tag | (version << 31) | done);
 			}
 		}
