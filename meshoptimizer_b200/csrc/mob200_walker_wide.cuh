@@ -269,7 +269,10 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 					const uint32_t win = rel & ~15u;
 					if (used & 0xeu)
 					{
-						wide_ring_ensure(ring, rel, lane);
+						// (the call above made the two chunks from rel's own readable: enough for the 528-byte window unless
+						// the header ended within 48 bytes of a chunk boundary)
+						if ((rel & (kWideChunk - 1)) > kWideChunk - 48 || (rel & (kWideChunk - 1)) < hdr)
+							wide_ring_ensure(ring, rel, lane);
 						uint32_t w[6];
 						{
 							uint32_t a = ring.sbase + ((win + lane * 16) & (kWideRingBytes - 1));
