@@ -368,178 +368,178 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 
 			if (do_stage)
 			{
-			// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
-			const long long c1 = dbg_clock();
-			mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 400);
-			if (i >= kSlots && freed < i - (kSlots - 1))
-				freed = i - (kSlots - 1);
+				// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
+				const long long c1 = dbg_clock();
+				mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 400);
+				if (i >= kSlots && freed < i - (kSlots - 1))
+					freed = i - (kSlots - 1);
 
-			if (valid)
-			{
-				const uint32_t enc_bytes = __shfl_sync(0xffffffffu, m_enc, j);
-				const uint32_t rows_bytes = vs <= kRowsInRingMaxVs ? 32u * vs : 0u;
-				const uint32_t len = enc_bytes + rows_bytes;
-
-				// allocate `len` contiguous bytes of the ring (pieces are freed in order)
-				uint32_t start;
-				for (;;)
+				if (valid)
 				{
-					uint32_t f = freed; // oldest live piece
-					while (f < i && ring_len[f & (kSlots - 1)] == 0)
-						++f;
-					if (f == i)
+					const uint32_t enc_bytes = __shfl_sync(0xffffffffu, m_enc, j);
+					const uint32_t rows_bytes = vs <= kRowsInRingMaxVs ? 32u * vs : 0u;
+					const uint32_t len = enc_bytes + rows_bytes;
+
+					// allocate `len` contiguous bytes of the ring (pieces are freed in order)
+					uint32_t start;
+					for (;;)
 					{
-						start = 0;
-						break;
-					}
-					const uint32_t so = ring_start[f & (kSlots - 1)];
-					if (head > so)
-					{
-						if (head + len <= kStageRingBytes)
-						{
-							start = head;
-							break;
-						}
-						if (len < so)
+						uint32_t f = freed; // oldest live piece
+						while (f < i && ring_len[f & (kSlots - 1)] == 0)
+							++f;
+						if (f == i)
 						{
 							start = 0;
 							break;
 						}
+						const uint32_t so = ring_start[f & (kSlots - 1)];
+						if (head > so)
+						{
+							if (head + len <= kStageRingBytes)
+							{
+								start = head;
+								break;
+							}
+							if (len < so)
+							{
+								start = 0;
+								break;
+							}
+						}
+						else if (head + len < so)
+						{
+							start = head;
+							break;
+						}
+						mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 400);
+						++freed;
 					}
-					else if (head + len < so)
+					dbg_slot += dbg_clock() - c1;
+					head = start + len;
+					// channel bytes: needed by the decoders from the start of the block
+					if (nq <= 8)
 					{
-						start = head;
-						break;
+						if (lane == j)
+							*reinterpret_cast<uint2*>(S.channels) = make_uint2(m_ch_lo, m_ch_hi);
 					}
-					mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 400);
-					++freed;
-				}
-				dbg_slot += dbg_clock() - c1;
-				head = start + len;
-				// channel bytes: needed by the decoders from the start of the block
-				if (nq <= 8)
-				{
+					else
+						for (uint32_t q = lane; q < nq; q += 32)
+							S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0;
+					__syncwarp();
 					if (lane == j)
-						*reinterpret_cast<uint2*>(S.channels) = make_uint2(m_ch_lo, m_ch_hi);
+					{
+						ring_start[slot] = start;
+						ring_len[slot] = len;
+						BlockParams& P = S.P;
+						const uint32_t groups = (m_n + kGroup - 1) / kGroup;
+						const uint32_t gshift = groups > 8 ? 4u : (groups > 4 ? 3u : (groups > 2 ? 2u : (groups > 1 ? 1u : 0u)));
+						P.valid = 1;
+						P.vs = vs;
+						P.n = m_n;
+						P.groups = groups;
+						P.gshift = gshift;
+						P.items = nq << gshift;
+						P.stage_off = start + m_shift;
+						P.rows_off = rows_bytes ? start + enc_bytes : kRowsInGlobal;
+						P.first = b == 0;
+						P.filter = m_filter;
+						P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs == 4) ? 1u : 2u);
+						P.m_chunk = magic_for(16 * vs);
+						P.out = reinterpret_cast<uint8_t*>(m_out);
+						P.rows_global = reinterpret_cast<const uint16_t*>(m_rows);
+						P.lookback = reinterpret_cast<unsigned long long*>(m_look);
+						if (kRounds)
+							P.round_members = round_members;
+
+						fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
+						mbar_expect_tx(full + slot, len);
+						tma_load_bulk(ring + start, reinterpret_cast<const void*>(m_lo), enc_bytes, full + slot);
+						if (rows_bytes)
+							tma_load_bulk(ring + start + enc_bytes, P.rows_global, rows_bytes, full + slot);
+					}
+					__syncwarp();
 				}
 				else
-					for (uint32_t q = lane; q < nq; q += 32)
-						S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0;
-				__syncwarp();
-				if (lane == j)
 				{
-					ring_start[slot] = start;
-					ring_len[slot] = len;
-					BlockParams& P = S.P;
-					const uint32_t groups = (m_n + kGroup - 1) / kGroup;
-					const uint32_t gshift = groups > 8 ? 4u : (groups > 4 ? 3u : (groups > 2 ? 2u : (groups > 1 ? 1u : 0u)));
-					P.valid = 1;
-					P.vs = vs;
-					P.n = m_n;
-					P.groups = groups;
-					P.gshift = gshift;
-					P.items = nq << gshift;
-					P.stage_off = start + m_shift;
-					P.rows_off = rows_bytes ? start + enc_bytes : kRowsInGlobal;
-					P.first = b == 0;
-					P.filter = m_filter;
-					P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs == 4) ? 1u : 2u);
-					P.m_chunk = magic_for(16 * vs);
-					P.out = reinterpret_cast<uint8_t*>(m_out);
-					P.rows_global = reinterpret_cast<const uint16_t*>(m_rows);
-					P.lookback = reinterpret_cast<unsigned long long*>(m_look);
-					if (kRounds)
-						P.round_members = round_members;
-
-					fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
-					mbar_expect_tx(full + slot, len);
-					tma_load_bulk(ring + start, reinterpret_cast<const void*>(m_lo), enc_bytes, full + slot);
-					if (rows_bytes)
-						tma_load_bulk(ring + start + enc_bytes, P.rows_global, rows_bytes, full + slot);
+					dbg_slot += dbg_clock() - c1;
+					__syncwarp();
+					if (lane == j)
+					{
+						ring_len[slot] = 0;
+						S.P.valid = 0;
+						if (kRounds)
+							S.P.round_members = round_members;
+						mbar_arrive(full + slot);
+					}
+					__syncwarp();
 				}
-				__syncwarp();
-			}
-			else
-			{
-				dbg_slot += dbg_clock() - c1;
-				__syncwarp();
-				if (lane == j)
-				{
-					ring_len[slot] = 0;
-					S.P.valid = 0;
-					if (kRounds)
-						S.P.round_members = round_members;
-					mbar_arrive(full + slot);
-				}
-				__syncwarp();
-			}
 
 			} // do_stage
 
 			// ---- carry into the block, per 4-byte lane ---------------------------------------------------------------
 			if (do_carry)
 			{
-			const long long c2 = dbg_clock();
-			bool carry_done = false;
-			if (valid && b > 0 && nq <= 8)
-			{
-				// the prefetched look-back entries: good if every one of them is an inclusive prefix of this run
-				const bool mine = (lane >> 1) == j;
-				const uint32_t q0 = (lane & 1u) * 4u;
-				const uint32_t want_flag = ((T.epoch & 0x3fffffffu) << 2) | 2u;
-				const bool good = (q0 >= nq || (uint32_t)(pre0 >> 32) == want_flag) && (q0 + 1 >= nq || (uint32_t)(pre1 >> 32) == want_flag) &&
-				                  (q0 + 2 >= nq || (uint32_t)(pre2 >> 32) == want_flag) && (q0 + 3 >= nq || (uint32_t)(pre3 >> 32) == want_flag);
-				carry_done = __all_sync(0xffffffffu, !mine || good);
-				if (carry_done && mine)
+				const long long c2 = dbg_clock();
+				bool carry_done = false;
+				if (valid && b > 0 && nq <= 8)
 				{
-					if (q0 < nq)
-						S.carry[q0] = (uint32_t)pre0;
-					if (q0 + 1 < nq)
-						S.carry[q0 + 1] = (uint32_t)pre1;
-					if (q0 + 2 < nq)
-						S.carry[q0 + 2] = (uint32_t)pre2;
-					if (q0 + 3 < nq)
-						S.carry[q0 + 3] = (uint32_t)pre3;
-				}
-			}
-			if (valid && !carry_done)
-			{
-				const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
-				for (uint32_t q = lane; q < nq; q += 32)
-				{
-					const uint32_t channel = S.channels[q];
-					uint32_t prefix;
-					if (b == 0)
+					// the prefetched look-back entries: good if every one of them is an inclusive prefix of this run
+					const bool mine = (lane >> 1) == j;
+					const uint32_t q0 = (lane & 1u) * 4u;
+					const uint32_t want_flag = ((T.epoch & 0x3fffffffu) << 2) | 2u;
+					const bool good = (q0 >= nq || (uint32_t)(pre0 >> 32) == want_flag) && (q0 + 1 >= nq || (uint32_t)(pre1 >> 32) == want_flag) &&
+					                  (q0 + 2 >= nq || (uint32_t)(pre2 >> 32) == want_flag) && (q0 + 3 >= nq || (uint32_t)(pre3 >> 32) == want_flag);
+					carry_done = __all_sync(0xffffffffu, !mine || good);
+					if (carry_done && mine)
 					{
-						// first vertex stored in the tail (:1846-1849)
-						const uint8_t* fv = tail + q * 4;
-						prefix = (uint32_t)__ldg(fv) | ((uint32_t)__ldg(fv + 1) << 8) | ((uint32_t)__ldg(fv + 2) << 16) | ((uint32_t)__ldg(fv + 3) << 24);
+						if (q0 < nq)
+							S.carry[q0] = (uint32_t)pre0;
+						if (q0 + 1 < nq)
+							S.carry[q0 + 1] = (uint32_t)pre1;
+						if (q0 + 2 < nq)
+							S.carry[q0 + 2] = (uint32_t)pre2;
+						if (q0 + 3 < nq)
+							S.carry[q0 + 3] = (uint32_t)pre3;
 					}
-					else
+				}
+				if (valid && !carry_done)
+				{
+					const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
+					for (uint32_t q = lane; q < nq; q += 32)
 					{
-						// decoupled look-back: add block aggregates (state 1) until an inclusive prefix (state 2)
-						const uint32_t Hq = lane_mask(channel);
-						prefix = 0;
-						const unsigned long long* prev = look + q - nq;
-						for (;;)
+						const uint32_t channel = S.channels[q];
+						uint32_t prefix;
+						if (b == 0)
 						{
-							const unsigned long long e = ld_volatile_u64(prev);
-							const uint32_t flag = (uint32_t)(e >> 32);
-							if ((flag >> 2) != (T.epoch & 0x3fffffffu) || (flag & 3u) == 0)
-								continue; // not published yet in this run
-							prefix = lane_combine(prefix, (uint32_t)e, Hq);
-							if ((flag & 3u) == 2)
-								break;
-							prev -= nq;
+							// first vertex stored in the tail (:1846-1849)
+							const uint8_t* fv = tail + q * 4;
+							prefix = (uint32_t)__ldg(fv) | ((uint32_t)__ldg(fv + 1) << 8) | ((uint32_t)__ldg(fv + 2) << 16) | ((uint32_t)__ldg(fv + 3) << 24);
 						}
+						else
+						{
+							// decoupled look-back: add block aggregates (state 1) until an inclusive prefix (state 2)
+							const uint32_t Hq = lane_mask(channel);
+							prefix = 0;
+							const unsigned long long* prev = look + q - nq;
+							for (;;)
+							{
+								const unsigned long long e = ld_volatile_u64(prev);
+								const uint32_t flag = (uint32_t)(e >> 32);
+								if ((flag >> 2) != (T.epoch & 0x3fffffffu) || (flag & 3u) == 0)
+									continue; // not published yet in this run
+								prefix = lane_combine(prefix, (uint32_t)e, Hq);
+								if ((flag & 3u) == 2)
+									break;
+								prev -= nq;
+							}
+						}
+						S.carry[q] = prefix;
 					}
-					S.carry[q] = prefix;
 				}
-			}
-			// every lane releases its own carry words (the barrier counts the 32 producer lanes)
-			mbar_arrive(carry_bar + slot);
-			__syncwarp();
-			dbg_look += dbg_clock() - c2;
+				// every lane releases its own carry words (the barrier counts the 32 producer lanes)
+				mbar_arrive(carry_bar + slot);
+				__syncwarp();
+				dbg_look += dbg_clock() - c2;
 			} // do_carry
 
 			if (!kRounds)
