@@ -187,6 +187,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 
 		if (lane == 0)
 			boff[0] = 1;
+		const uint32_t publish_every = vs <= 8 ? 4u : (vs <= 16 ? 2u : 1u);
 		for (uint32_t b = 0; b < nblocks && status == 0; ++b)
 		{
 			const uint32_t n = min(bv, count - b * bv);
@@ -351,8 +352,11 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 			done = b + 1;
 			__syncwarp();
 			if (lane == 0)
-			{
 				boff[b + 1] = rel - rel0;
+			// blocks of small vertices are published in groups (a release is a MEMBAR.GPU: several hundred cycles next to
+			// the ~850 per byte-channel of a block that has only 4 ... 16 of them)
+			if (lane == 0 && ((done & (publish_every - 1u)) == 0 || done == nblocks))
+			{
 				// (the table rows were written by other lanes before the __syncwarp above: the release below is a
 				// fence + store and cumulative over what this lane has synchronised with, so no fence of its own is
 				// needed here -- a second MEMBAR.GPU per block was a fifth of the walk of a 4-byte-vertex stream)
@@ -372,7 +376,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 		{
 			for (uint32_t b = framed ? done + 1 : 0; b <= nblocks; ++b)
 				boff[b] = kInvalidOffset;
-			st_release_u64(progress, tag | nblocks);
+			st_release_u64(progress, tag | ((version & 1u) << 31) | nblocks); // (blocks walked before the failure may still be waiting for their release)
 		}
 		T.status[d->caller_index] = status;
 	}
