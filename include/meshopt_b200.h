@@ -95,13 +95,56 @@ MESHOPTIMIZER_API void mob200_context_destroy(mob200_Context* ctx);
 MESHOPTIMIZER_API int mob200_plan_create(mob200_Context* ctx, const mob200_Stream* streams, size_t n, mob200_Plan** out);
 MESHOPTIMIZER_API void mob200_plan_destroy(mob200_Plan* plan);
 
-/* Enqueue walk + decode(+filter) kernels for the whole batch on `cuda_stream`; asynchronous.
- * May be called repeatedly (every call decodes the batch again). */
+/* Enqueue the fused walk + decode(+filter) kernel for the whole batch on `cuda_stream`; asynchronous.
+ * May be called repeatedly (every call walks and decodes the batch again).
+ * The kernel is persistent and its roles wait for each other across CTAs: all its CTAs must be resident at the same
+ * time.  The launch therefore takes at most one CTA per SM of the device, and runs of plans that may overlap in time
+ * (different streams) are serialised by the library with an event chain per context. */
 MESHOPTIMIZER_API int mob200_plan_run(mob200_Plan* plan, void* cuda_stream);
 
 /* Wait for the last run on `cuda_stream` and copy one reference return code per stream to
  * status[n] (host).  Returns the number of streams whose code is non-zero, or MOB200_ERR_CUDA. */
 MESHOPTIMIZER_API int mob200_plan_status(mob200_Plan* plan, int* status, void* cuda_stream);
+
+/* ---- 2b. block-offset sidecar: walk parallelism for few long streams ---------------------------------------------
+ *
+ * A stream stores no index, so finding where block b starts means walking blocks 0 .. b-1 (reference
+ * src/vertexcodec.cpp:1857-1866 advances one pointer); one long stream is therefore one serial chain, however many
+ * SMs there are.  The SIDECAR of a stream is the table of those offsets: mob200_sidecar_entries() = nblocks + 1
+ * unsigned ints, entry b = byte offset of block b from the start of the stream (entry 0 is 1: the header byte),
+ * entry nblocks = where the last block ends (= buffer_size - padded tail).  4 bytes per <= 8 KB of vertices.
+ * With it every block is walked by its own GPU lane ("block mode"): one monolithic stream decodes as fast as
+ * thousands of short ones.  A sidecar is never trusted: each lane checks that its block ends exactly where the
+ * next one is said to start, block 0 at byte 1, the last one at the tail -- the verified blocks then are the very
+ * chain the serial walk follows.  A stream whose sidecar does not fit (stale, corrupt, or the stream itself is
+ * malformed) gets status MOB200_ERR_SIDECAR and must be decoded again without it to obtain the reference code.
+ *
+ * Where a sidecar comes from: (a) mob200_plan_export_sidecar after a run of the serial walk (store it next to the
+ * asset; decode with it ever after); (b) the encoder-side helper mob200_encode_segments, which emits it;
+ * (c) implicitly: any plan that has run once keeps its offsets, and mob200_plan_run_ex(.., MOB200_RUN_BLOCK_PARALLEL)
+ * decodes the same plan again in block mode (re-verifying them: changed input bytes are caught).
+ */
+#define MOB200_ERR_SIDECAR (-102)         /* per-stream status: the block-offset sidecar does not describe this stream */
+#define MOB200_RUN_BLOCK_PARALLEL 1       /* mob200_plan_run_ex flag: walk every block from the plan's offset table */
+
+/* nblocks + 1 (0 for an empty stream or an illegal vertex size) */
+MESHOPTIMIZER_API size_t mob200_sidecar_entries(size_t vertex_count, size_t vertex_size);
+
+/* mob200_plan_create with one HOST sidecar pointer per stream (sidecars[i] has mob200_sidecar_entries(..) entries; it
+ * may be NULL only for streams without vertices -- if any other stream lacks one the plan is created without
+ * offsets).  The offsets are uploaded once; mob200_plan_run_ex(.., MOB200_RUN_BLOCK_PARALLEL) uses them. */
+MESHOPTIMIZER_API int mob200_plan_create_sidecar(mob200_Context* ctx, const mob200_Stream* streams, size_t n, const unsigned int* const* sidecars, mob200_Plan** out);
+
+/* mob200_plan_run with flags.  MOB200_RUN_BLOCK_PARALLEL needs offsets in the plan (mob200_plan_has_offsets), else
+ * MOB200_ERR_ARGUMENT.  Status codes of a block-mode run: 0, the framing codes -1 / -2 / -3 of streams whose
+ * header, size or tail is wrong, and MOB200_ERR_SIDECAR. */
+MESHOPTIMIZER_API int mob200_plan_run_ex(mob200_Plan* plan, void* cuda_stream, int flags);
+MESHOPTIMIZER_API int mob200_plan_has_offsets(const mob200_Plan* plan);
+
+/* Copy the sidecar of stream `stream_index` (caller order) out of the plan after a run on `cuda_stream`
+ * (synchronises on it).  Returns the number of entries written, MOB200_ERR_ARGUMENT if capacity is too small, or
+ * MOB200_ERR_SIDECAR if that stream's walk failed (its offsets are not a sidecar). */
+MESHOPTIMIZER_API int mob200_plan_export_sidecar(mob200_Plan* plan, size_t stream_index, unsigned int* out, size_t capacity, void* cuda_stream);
 
 /* Number of kernels one mob200_plan_run enqueues (for launch accounting). */
 MESHOPTIMIZER_API int mob200_plan_launches(const mob200_Plan* plan);
@@ -124,15 +167,19 @@ MESHOPTIMIZER_API int mob200_filter_device(int filter, void* device_buffer, size
 MESHOPTIMIZER_API int mob200_context_sm_count(const mob200_Context* ctx);
 MESHOPTIMIZER_API const char* mob200_version(void);
 
-/* Duration in milliseconds of the kernels of the most recent mob200_plan_run, measured with CUDA
- * events recorded on the launching stream around (0) the whole run, (1) the walk kernel, (2) the
- * decode kernel.  Synchronises on the end event.  Returns 0 or MOB200_ERR_CUDA. */
-MESHOPTIMIZER_API int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float* ms_walk, float* ms_decode);
+/* Duration in milliseconds of the most recent mob200_plan_run: ONE fused persistent kernel (walker, producer and
+ * decoder warps), measured with a pair of CUDA events recorded on the launching stream around the launch.
+ * Synchronises on the end event.  Returns 0 or MOB200_ERR_CUDA. */
+MESHOPTIMIZER_API int mob200_plan_last_timing(mob200_Plan* plan, float* ms);
 
-/* Same for the most recent runs (at most 64 are remembered, oldest first): fills up to max_runs
- * entries of each non-NULL array and returns how many were written.  Nothing is synchronised until
- * this call, so a timed region of repeated mob200_plan_run calls stays asynchronous. */
-MESHOPTIMIZER_API int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms_total, float* ms_walk, float* ms_decode);
+/* Same for the most recent runs (at most 64 are remembered, oldest first): fills up to max_runs entries of ms and
+ * returns how many were written.  Nothing is synchronised until this call, so a timed region of repeated
+ * mob200_plan_run calls stays asynchronous. */
+MESHOPTIMIZER_API int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms);
+
+/* Host milliseconds mob200_plan_create spent on this plan (validation, sort, decode order, table uploads): the
+ * one-off cost a single-shot decode pays in front of the kernel. */
+MESHOPTIMIZER_API float mob200_plan_create_ms(const mob200_Plan* plan);
 
 /* Diagnostics: cycle counters the kernel accumulates over all CTAs since the last reset -- [0] decoder
  * warps total, [1..3] of which waiting for staged data / the cross-block carry / the output tile, [4]

@@ -32,7 +32,8 @@ _FILTER_BY_NAME = {
     "EXPONENTIAL": 3, "exp": 3,
     "COLOR": 4, "color": 4,
 }
-ERR_CUDA, ERR_ARGUMENT = -100, -101
+ERR_CUDA, ERR_ARGUMENT, ERR_SIDECAR = -100, -101, -102
+RUN_BLOCK_PARALLEL = 1
 
 
 INDEX_TRIANGLES, INDEX_SEQUENCE = 0, 1
@@ -105,7 +106,8 @@ EXPORTS = [
     "mob200_context_create", "mob200_context_destroy", "mob200_plan_create", "mob200_plan_destroy",
     "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
     "mob200_decode_batch_host", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
-    "mob200_plan_last_timing", "mob200_plan_timing_history", "mob200_plan_debug_counters",
+    "mob200_plan_last_timing", "mob200_plan_timing_history", "mob200_plan_debug_counters", "mob200_plan_create_ms",
+    "mob200_sidecar_entries", "mob200_plan_create_sidecar", "mob200_plan_run_ex", "mob200_plan_has_offsets", "mob200_plan_export_sidecar",
     "meshopt_decodeIndexBuffer", "meshopt_decodeIndexVersion", "meshopt_decodeIndexSequence",
     "mob200_decode_index_batch_device", "mob200_decode_index_batch_host",
     "mob200_gltf_scan", "mob200_gltf_decode_host", "mob200_gltf_decode_device",
@@ -150,11 +152,23 @@ def lib() -> ctypes.CDLL:
     L.mob200_plan_launches.restype = c_int
     L.mob200_plan_launches.argtypes = [c_void_p]
     L.mob200_plan_last_timing.restype = c_int
-    L.mob200_plan_last_timing.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+    L.mob200_plan_last_timing.argtypes = [c_void_p, POINTER(c_float)]
+    L.mob200_plan_create_ms.restype = c_float
+    L.mob200_plan_create_ms.argtypes = [c_void_p]
+    L.mob200_sidecar_entries.restype = c_size_t
+    L.mob200_sidecar_entries.argtypes = [c_size_t, c_size_t]
+    L.mob200_plan_create_sidecar.restype = c_int
+    L.mob200_plan_create_sidecar.argtypes = [c_void_p, POINTER(Stream), c_size_t, POINTER(c_void_p), POINTER(c_void_p)]
+    L.mob200_plan_run_ex.restype = c_int
+    L.mob200_plan_run_ex.argtypes = [c_void_p, c_void_p, c_int]
+    L.mob200_plan_has_offsets.restype = c_int
+    L.mob200_plan_has_offsets.argtypes = [c_void_p]
+    L.mob200_plan_export_sidecar.restype = c_int
+    L.mob200_plan_export_sidecar.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]
     L.mob200_plan_debug_counters.restype = c_int
     L.mob200_plan_debug_counters.argtypes = [c_void_p, POINTER(ctypes.c_ulonglong), c_int, c_int]
     L.mob200_plan_timing_history.restype = c_int
-    L.mob200_plan_timing_history.argtypes = [c_void_p, c_int, POINTER(c_float), POINTER(c_float), POINTER(c_float)]
+    L.mob200_plan_timing_history.argtypes = [c_void_p, c_int, POINTER(c_float)]
     L.mob200_decode_batch_device.restype = c_int
     L.mob200_decode_batch_device.argtypes = [c_void_p, POINTER(Stream), c_size_t, c_void_p]
     L.mob200_decode_batch_host.restype = c_int
@@ -330,21 +344,46 @@ def make_streams(items: Sequence[tuple]) -> ctypes.Array:
 
 
 class Plan:
-    """``mob200_Plan``: a prepared batch of device-resident streams that can be run repeatedly."""
+    """``mob200_Plan``: a prepared batch of device-resident streams that can be run repeatedly.
 
-    def __init__(self, ctx: Context, streams: ctypes.Array):
+    ``sidecars``: optional list with one uint32 array (``sidecar_entries(count, size)`` block offsets) or ``None``
+    per stream; with them ``run(block_parallel=True)`` walks every block on its own GPU lane."""
+
+    def __init__(self, ctx: Context, streams: ctypes.Array, sidecars: Optional[Sequence] = None):
         self.ctx = ctx
         self.n = len(streams)
         h = c_void_p()
-        rc = lib().mob200_plan_create(ctx.handle, streams, self.n, ctypes.byref(h))
+        if sidecars is None:
+            rc = lib().mob200_plan_create(ctx.handle, streams, self.n, ctypes.byref(h))
+        else:
+            assert len(sidecars) == self.n
+            keep = [None if sc is None else np.ascontiguousarray(sc, dtype=np.uint32) for sc in sidecars]
+            ptrs = (c_void_p * max(self.n, 1))()
+            for i, sc in enumerate(keep):
+                if sc is not None:
+                    assert sc.size == sidecar_entries(streams[i].vertex_count, streams[i].vertex_size), "sidecar length"
+                    ptrs[i] = sc.ctypes.data
+            rc = lib().mob200_plan_create_sidecar(ctx.handle, streams, self.n, ptrs, ctypes.byref(h))
         if rc != 0:
             raise RuntimeError(f"mob200_plan_create failed ({rc})")
         self.handle = h
 
-    def run(self, cuda_stream: int = 0) -> None:
-        rc = lib().mob200_plan_run(self.handle, c_void_p(cuda_stream))
+    def run(self, cuda_stream: int = 0, block_parallel: bool = False) -> None:
+        rc = lib().mob200_plan_run_ex(self.handle, c_void_p(cuda_stream), RUN_BLOCK_PARALLEL if block_parallel else 0)
         if rc != 0:
             raise RuntimeError(f"mob200_plan_run failed ({rc})")
+
+    @property
+    def has_offsets(self) -> bool:
+        return bool(lib().mob200_plan_has_offsets(self.handle))
+
+    def export_sidecar(self, stream_index: int, vertex_count: int, vertex_size: int, cuda_stream: int = 0) -> np.ndarray:
+        """block offsets of one stream after a run of the serial walk (raises if that stream's walk failed)"""
+        out = np.zeros(max(1, sidecar_entries(vertex_count, vertex_size)), dtype=np.uint32)
+        rc = lib().mob200_plan_export_sidecar(self.handle, stream_index, out.ctypes.data, out.size, c_void_p(cuda_stream))
+        if rc < 0:
+            raise RuntimeError(f"mob200_plan_export_sidecar failed ({rc})")
+        return out[:rc]
 
     def status(self, cuda_stream: int = 0) -> np.ndarray:
         st = np.zeros(max(self.n, 1), dtype=np.int32)
@@ -357,12 +396,17 @@ class Plan:
     def launches(self) -> int:
         return int(lib().mob200_plan_launches(self.handle))
 
-    def last_timing(self):
-        a, b, c = c_float(), c_float(), c_float()
-        rc = lib().mob200_plan_last_timing(self.handle, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    @property
+    def create_ms(self) -> float:
+        return float(lib().mob200_plan_create_ms(self.handle))
+
+    def last_timing(self) -> float:
+        """milliseconds of the most recent run's kernel (CUDA events on the launching stream)"""
+        a = c_float()
+        rc = lib().mob200_plan_last_timing(self.handle, ctypes.byref(a))
         if rc != 0:
             raise RuntimeError(f"mob200_plan_last_timing failed ({rc})")
-        return {"total_ms": a.value, "walk_ms": b.value, "decode_ms": c.value}
+        return a.value
 
     def debug_counters(self, reset: bool = True):
         """cycle counters accumulated by the kernel (see mob200_plan_debug_counters)"""
@@ -375,12 +419,12 @@ class Plan:
         return dict(zip(names, [int(v) for v in out]))
 
     def timing_history(self, max_runs: int = 64):
-        """per-run kernel durations (ms) of the most recent runs, oldest first"""
-        a, b, c = (c_float * max_runs)(), (c_float * max_runs)(), (c_float * max_runs)()
-        n = lib().mob200_plan_timing_history(self.handle, max_runs, a, b, c)
+        """kernel durations (ms) of the most recent runs, oldest first"""
+        a = (c_float * max_runs)()
+        n = lib().mob200_plan_timing_history(self.handle, max_runs, a)
         if n < 0:
             raise RuntimeError(f"mob200_plan_timing_history failed ({n})")
-        return [{"total_ms": a[i], "walk_ms": b[i], "decode_ms": c[i]} for i in range(n)]
+        return [float(a[i]) for i in range(n)]
 
     def close(self) -> None:
         if self.handle:
@@ -392,6 +436,10 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def sidecar_entries(vertex_count: int, vertex_size: int) -> int:
+    return int(lib().mob200_sidecar_entries(vertex_count, vertex_size))
 
 
 def decode_batch_host(items: Iterable[tuple], ctx: Optional[Context] = None):

@@ -12,6 +12,7 @@
 #include "mob200_kernels.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,11 +31,18 @@ struct mob200_Plan
 	void* arena = nullptr;
 	bool owns_arena = true;
 	uint32_t grid = 0;
-	// ring of CUDA-event triples (before walk, between, after decode), one per run, recorded on the
-	// launching stream: per-kernel durations can be read back after a timed region without any
+	// block-offset sidecar: position of every caller stream in the sorted device array, and whether the block_offset
+	// table holds offsets a block-mode run may start from (imported, or left by a run of the serial walk)
+	std::vector<uint32_t> sorted_of_caller;
+	std::vector<uint32_t> stream_nblocks, stream_block_base; // per sorted stream
+	bool have_offsets = false;
+	int wide_walk_choice = 0, rounds_choice = 0;
+	// ring of CUDA-event pairs (before / after the fused walk + decode kernel), one per run, recorded on the
+	// launching stream: per-launch durations can be read back after a timed region without any
 	// synchronisation inside it
 	static const int kRing = 64;
-	cudaEvent_t ev[kRing][3] = {};
+	cudaEvent_t ev[kRing][2] = {};
+	float create_ms = 0.f; // host time spent in mob200_plan_create (sort, tables, uploads)
 	unsigned long long runs = 0;
 };
 
@@ -132,7 +140,21 @@ static size_t align_up(size_t v, size_t a)
 
 // ext_arena != NULL: the tables live in a caller-owned, grow-only buffer, their initialisation is only
 // ENQUEUED on init_stream (the plan must then run on that stream), and no timing events are created.
-static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, size_t n, DeviceBuffer* ext_arena, cudaStream_t init_stream, bool timing, mob200_Plan** out)
+static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, size_t n, DeviceBuffer* ext_arena, cudaStream_t init_stream, bool timing, mob200_Plan** out,
+    const unsigned int* const* sidecars);
+
+static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, size_t n, DeviceBuffer* ext_arena, cudaStream_t init_stream, bool timing, mob200_Plan** out,
+    const unsigned int* const* sidecars = nullptr)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	const int rc = plan_create_body(ctx, streams, n, ext_arena, init_stream, timing, out, sidecars);
+	if (rc == 0 && out && *out)
+		(*out)->create_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	return rc;
+}
+
+static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, size_t n, DeviceBuffer* ext_arena, cudaStream_t init_stream, bool timing, mob200_Plan** out,
+    const unsigned int* const* sidecars)
 {
 	if (!ctx || !out || (n && !streams) || n >= 0xffffffffull)
 		return MOB200_ERR_ARGUMENT;
@@ -165,6 +187,7 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	});
 
 	std::vector<DevStream> host(n);
+	size_t n_with_blocks = 0;
 	uint64_t total_blocks = 0, total_chan = 0, small_blocks = 0; // small: a block of <= 12-byte vertices (one or two work quanta of the decoders; 16-byte blocks gain nothing from rounds)
 	for (size_t i = 0; i < n; ++i)
 	{
@@ -181,6 +204,8 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 		d.filter = (uint8_t)s.filter;
 		d.block_groups = (uint8_t)(block_vertices((uint32_t)s.vertex_size) / kGroup);
 		d.caller_index = order[i];
+		if (d.nblocks)
+			n_with_blocks = i + 1;
 		total_blocks += d.nblocks;
 		small_blocks += s.vertex_size <= 12 ? d.nblocks : 0;
 		total_chan += (uint64_t)d.nblocks * s.vertex_size;
@@ -226,8 +251,8 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	size_t off_streams = 0;
 	size_t off_boff = align_up(off_streams + n * sizeof(DevStream), 256);
 	size_t off_table = align_up(off_boff + (total_blocks + n) * 4, 256);
-	size_t off_progress = align_up(off_table + total_chan * 32, 256);
-	size_t off_look = align_up(off_progress + n * 8, 256);
+	size_t off_ready = align_up(off_table + total_chan * 32, 256);
+	size_t off_look = align_up(off_ready + total_blocks * 4, 256);
 	size_t off_tinfo = align_up(off_look + (total_chan / 4) * 8, 256);
 	size_t off_status = align_up(off_tinfo + total_blocks * 8, 256);
 	size_t off_counters = align_up(off_status + n * 4, 256);
@@ -253,13 +278,15 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.streams = reinterpret_cast<DevStream*>(base + off_streams);
 	plan->T.block_offset = reinterpret_cast<uint32_t*>(base + off_boff);
 	plan->T.group_table = reinterpret_cast<uint16_t*>(base + off_table);
-	plan->T.progress = reinterpret_cast<unsigned long long*>(base + off_progress);
+	plan->T.block_ready = reinterpret_cast<uint32_t*>(base + off_ready);
 	plan->T.lookback = reinterpret_cast<unsigned long long*>(base + off_look);
 	plan->T.ticket_info = reinterpret_cast<uint2*>(base + off_tinfo);
 	plan->T.status = reinterpret_cast<int32_t*>(base + off_status);
 	plan->T.counters = reinterpret_cast<uint32_t*>(base + off_counters);
 	plan->T.n_streams = (uint32_t)n;
+	plan->T.n_with_blocks = (uint32_t)n_with_blocks;
 	plan->T.total_blocks = (uint32_t)total_blocks;
+	plan->T.block_mode = 0;
 	plan->T.units = plan->grid;
 	plan->T.epoch = 0;
 	plan->T.walker_lead = ctx->walker_lead;
@@ -268,12 +295,23 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	// pace and a round only waits longer for its members: measured 5-15% slower at 1024 streams): decode in rounds
 	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && n >= (size_t)8 * plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
 	plan->T.wide_walk = ctx->wide_walk_mode == 2 ? (n < (size_t)2 * resident ? 1u : 0u) : (uint32_t)ctx->wide_walk_mode;
+	plan->wide_walk_choice = (int)plan->T.wide_walk;
+	plan->rounds_choice = (int)plan->T.rounds;
+	plan->sorted_of_caller.assign(n, 0);
+	plan->stream_nblocks.resize(n);
+	plan->stream_block_base.resize(n);
+	for (size_t i = 0; i < n; ++i)
+	{
+		plan->sorted_of_caller[order[i]] = (uint32_t)i;
+		plan->stream_nblocks[i] = host[i].nblocks;
+		plan->stream_block_base[i] = host[i].block_base;
+	}
 
 	// table initialisation is enqueued on the context's stream and waited for, so that a later
 	// mob200_plan_run on any stream sees it (cudaMemset on device memory may return early)
 	bool ok = true;
 	cudaStream_t st = init_stream;
-	ok = ok && cudaMemsetAsync(base + off_progress, 0, n * 8, st) == cudaSuccess;             // epoch 0 = never published
+	ok = ok && cudaMemsetAsync(base + off_ready, 0, total_blocks * 4, st) == cudaSuccess;      // epoch 0 = never published
 	ok = ok && cudaMemsetAsync(base + off_look, 0, (total_chan / 4) * 8, st) == cudaSuccess;
 	ok = ok && cudaMemsetAsync(base + off_counters, 0, 256, st) == cudaSuccess;
 	if (n)
@@ -282,11 +320,37 @@ static int plan_create_impl(mob200_Context* ctx, const mob200_Stream* streams, s
 	{
 		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
 	}
+	std::vector<uint32_t> side; // (must outlive the asynchronous copy: synchronised below)
+	if (sidecars)
+	{
+		// block-offset sidecars: stream i (sorted) owns entries [block_base + i, block_base + i + nblocks] of the table;
+		// a stream without a sidecar makes the whole plan fall back to the serial walk
+		bool all = true;
+		side.assign(total_blocks + n, kInvalidOffset);
+		for (size_t i = 0; i < n && all; ++i)
+		{
+			const unsigned int* sc = sidecars[order[i]];
+			if (host[i].nblocks == 0)
+				continue;
+			if (!sc)
+			{
+				all = false;
+				break;
+			}
+			memcpy(side.data() + host[i].block_base + i, sc, ((size_t)host[i].nblocks + 1) * 4);
+		}
+		if (all && total_blocks)
+		{
+			ok = ok && cudaMemcpyAsync(base + off_boff, side.data(), side.size() * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+			ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+			plan->have_offsets = true;
+		}
+	}
 	if (!ext_arena)
 		ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
 	if (timing)
 		for (int r = 0; r < mob200_Plan::kRing; ++r)
-			for (int i = 0; i < 3; ++i)
+			for (int i = 0; i < 2; ++i)
 				ok = ok && cudaEventCreate(&plan->ev[r][i]) == cudaSuccess;
 	if (!ok)
 	{
@@ -310,7 +374,7 @@ extern "C" void mob200_plan_destroy(mob200_Plan* plan)
 		return;
 	cudaSetDevice(plan->ctx->device);
 	for (int r = 0; r < mob200_Plan::kRing; ++r)
-		for (int i = 0; i < 3; ++i)
+		for (int i = 0; i < 2; ++i)
 			if (plan->ev[r][i])
 				cudaEventDestroy(plan->ev[r][i]);
 	if (plan->arena && plan->owns_arena)
@@ -323,13 +387,100 @@ extern "C" int mob200_plan_launches(const mob200_Plan* plan)
 	return (plan && plan->n) ? 1 : 0; // one fused persistent kernel per run
 }
 
+extern "C" int mob200_plan_create_sidecar(mob200_Context* ctx, const mob200_Stream* streams, size_t n, const unsigned int* const* sidecars, mob200_Plan** out)
+{
+	if (!ctx)
+		return MOB200_ERR_ARGUMENT;
+	return plan_create_impl(ctx, streams, n, nullptr, ctx->stream, true, out, sidecars);
+}
+
+extern "C" size_t mob200_sidecar_entries(size_t vertex_count, size_t vertex_size)
+{
+	if (vertex_size == 0 || vertex_size > 256 || vertex_size % 4 != 0)
+		return 0;
+	const size_t bv = block_vertices((uint32_t)vertex_size);
+	const size_t nblocks = (vertex_count + bv - 1) / bv;
+	return nblocks ? nblocks + 1 : 0;
+}
+
+extern "C" int mob200_plan_has_offsets(const mob200_Plan* plan)
+{
+	return plan && plan->have_offsets ? 1 : 0;
+}
+
+extern "C" int mob200_plan_export_sidecar(mob200_Plan* plan, size_t stream_index, unsigned int* out, size_t capacity, void* cuda_stream)
+{
+	if (!plan || stream_index >= plan->n || (!out && capacity))
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	const uint32_t i = plan->sorted_of_caller[stream_index];
+	const size_t entries = plan->stream_nblocks[i] ? (size_t)plan->stream_nblocks[i] + 1 : 0;
+	if (capacity < entries)
+		return MOB200_ERR_ARGUMENT;
+	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+	if (entries)
+		CUDA_TRY(cudaMemcpyAsync(out, plan->T.block_offset + plan->stream_block_base[i] + i, entries * 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	// a stream whose serial walk failed has kInvalidOffset entries: not a usable sidecar
+	for (size_t k = 0; k < entries; ++k)
+		if (out[k] == kInvalidOffset)
+			return MOB200_ERR_SIDECAR;
+	return (int)entries;
+}
+
 extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
+{
+	return mob200_plan_run_ex(plan, cuda_stream, 0);
+}
+
+// The decode kernel is persistent and its warp roles wait for each other across CTAs (walker -> producer ->
+// decoder, look-back between units): every CTA of a launch must be resident.  One launch alone always is (the
+// grid is sized from the occupancy query), two launches that share the device might each hold only part of their
+// CTAs and wait for the rest forever.  Launches of this library on one device are therefore chained with an event:
+// the kernels of different contexts / CUDA streams run one after the other, copies still overlap them.
+struct DeviceSerial
+{
+	std::mutex mu;
+	cudaEvent_t last = nullptr;
+	bool recorded = false;
+};
+static DeviceSerial g_serial[64];
+
+static int launch_serialised(const mob200_Context* ctx, const DevTables& T, uint32_t ctas, cudaStream_t st, cudaEvent_t before, cudaEvent_t after)
+{
+	DeviceSerial& ds = g_serial[ctx->device & 63];
+	std::lock_guard<std::mutex> lock(ds.mu);
+	if (!ds.last)
+		CUDA_TRY(cudaEventCreateWithFlags(&ds.last, cudaEventDisableTiming));
+	if (ds.recorded)
+		CUDA_TRY(cudaStreamWaitEvent(st, ds.last, 0));
+	if (before)
+		CUDA_TRY(cudaEventRecord(before, st));
+	CUDA_TRY(launch_decode(T, ctas, st));
+	if (after)
+		CUDA_TRY(cudaEventRecord(after, st));
+	CUDA_TRY(cudaEventRecord(ds.last, st));
+	ds.recorded = true;
+	return 0;
+}
+
+extern "C" int mob200_plan_run_ex(mob200_Plan* plan, void* cuda_stream, int flags)
 {
 	if (!plan)
 		return MOB200_ERR_ARGUMENT;
 	if (set_device(plan->ctx))
 		return MOB200_ERR_CUDA;
 	cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+	const bool block_mode = (flags & MOB200_RUN_BLOCK_PARALLEL) != 0;
+	if (block_mode && !plan->have_offsets)
+		return MOB200_ERR_ARGUMENT; // no sidecar was imported and no serial walk has run yet
+	plan->T.block_mode = block_mode ? 1u : 0u;
+	plan->T.wide_walk = block_mode ? 0u : (uint32_t)plan->wide_walk_choice; // block mode: one walker lane per block
+	if (block_mode && plan->n)
+		CUDA_TRY(cudaMemsetAsync(plan->T.status, 0, plan->n * sizeof(int32_t), st)); // block mode reports failures only
+	if (!block_mode)
+		plan->have_offsets = true; // the serial walk leaves every block's offset in the table (a failed stream is caught when the table is used)
 	const bool reuse_tables = plan->T.walker_lead == kDecodeOnly || plan->T.walker_lead == kRewalk;
 	if (!reuse_tables || plan->runs == 0) // (decode-only diagnostics: reuse the tables of the first run)
 	{
@@ -343,22 +494,16 @@ extern "C" int mob200_plan_run(mob200_Plan* plan, void* cuda_stream)
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
 	const bool timed = ev[0] != nullptr;
-	if (timed)
-	{
-		CUDA_TRY(cudaEventRecord(ev[0], st));
-		CUDA_TRY(cudaEventRecord(ev[1], st)); // (kept for the timing interface: the walk is fused into the decode kernel)
-	}
 	// unit u runs in CTA u % ctas: a batch with few units still spreads over all SMs
 	const uint32_t ctas_max = (uint32_t)(plan->ctx->sm_count * plan->ctx->decode_ctas_per_sm);
 	const uint32_t ctas = std::max<uint32_t>((plan->grid + kUnitsPerCta - 1) / kUnitsPerCta, std::min<uint32_t>(ctas_max, plan->grid));
-	CUDA_TRY(launch_decode(T, ctas, st));
-	if (timed)
-		CUDA_TRY(cudaEventRecord(ev[2], st));
+	if (launch_serialised(plan->ctx, T, ctas, st, timed ? ev[0] : nullptr, timed ? ev[1] : nullptr))
+		return MOB200_ERR_CUDA;
 	plan->runs++;
 	return 0;
 }
 
-extern "C" int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms_total, float* ms_walk, float* ms_decode)
+extern "C" int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float* ms)
 {
 	if (!plan || max_runs < 0 || !plan->ev[0][0])
 		return MOB200_ERR_ARGUMENT;
@@ -371,25 +516,24 @@ extern "C" int mob200_plan_timing_history(mob200_Plan* plan, int max_runs, float
 		// i = 0 is the oldest of the `count` most recent runs
 		unsigned long long run = plan->runs - count + i;
 		cudaEvent_t* ev = plan->ev[run % mob200_Plan::kRing];
-		CUDA_TRY(cudaEventSynchronize(ev[2]));
-		float a = 0, b = 0, c = 0;
-		CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[2]));
-		CUDA_TRY(cudaEventElapsedTime(&b, ev[0], ev[1]));
-		CUDA_TRY(cudaEventElapsedTime(&c, ev[1], ev[2]));
-		if (ms_total)
-			ms_total[i] = a;
-		if (ms_walk)
-			ms_walk[i] = b;
-		if (ms_decode)
-			ms_decode[i] = c;
+		CUDA_TRY(cudaEventSynchronize(ev[1]));
+		float a = 0;
+		CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[1]));
+		if (ms)
+			ms[i] = a;
 	}
 	return count;
 }
 
-extern "C" int mob200_plan_last_timing(mob200_Plan* plan, float* ms_total, float* ms_walk, float* ms_decode)
+extern "C" int mob200_plan_last_timing(mob200_Plan* plan, float* ms)
 {
-	int n = mob200_plan_timing_history(plan, 1, ms_total, ms_walk, ms_decode);
+	int n = mob200_plan_timing_history(plan, 1, ms);
 	return n == 1 ? 0 : (n < 0 ? n : MOB200_ERR_ARGUMENT);
+}
+
+extern "C" float mob200_plan_create_ms(const mob200_Plan* plan)
+{
+	return plan ? plan->create_ms : 0.f;
 }
 
 extern "C" int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset)

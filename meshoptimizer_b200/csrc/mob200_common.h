@@ -76,18 +76,26 @@ struct DevTables
 	                              // by the walker warps, read by the decoders.
 	uint16_t* group_table;        // per (block, byte-channel): 16 entries, one per 16-value group:
 	                              // 0 = all zero, else (offset_in_block << 2) | log2(bits).  Walker -> decoder.
-	unsigned long long* progress; // [n_streams]: epoch << 32 | codec version << 31 | number of blocks walked (release/acquire)
+	uint32_t* block_ready;        // [total_blocks], block b of stream s at block_base + b: (epoch << 2) | codec version << 1 | decodable,
+	                              // release-stored by the walker that walked (normal mode) or verified (block mode) the block,
+	                              // acquire-polled by the producers
 	unsigned long long* lookback; // per block, vertex_size/4 entries: (epoch << 2 | state) << 32 | value
 	const uint2* ticket_info;     // [total_blocks]: decode order -> (stream, block)
 	int32_t* status;              // [n_streams] in CALLER order: reference return code per stream
 	uint32_t* counters;           // [0] decode ticket, [1] walker stream ticket, [2] finished roles
 	uint32_t n_streams;
+	uint32_t n_with_blocks;       // streams [0, n_with_blocks) of the sorted array have at least one block
 	uint32_t total_blocks;
 	uint32_t units;               // decode units that take part in this run (unit u decodes tickets u, u + units, ...)
 	uint32_t epoch;               // changes every run, so progress / look-back entries never need clearing
 	uint32_t walker_lead;         // 0xffffffff = walk-only diagnostic mode (decoders off); otherwise unused
 	uint32_t wide_walk;           // 1: one warp per stream (few streams), 0: one lane per stream (many streams)
 	uint32_t rounds;              // 1: most blocks are small-vertex blocks (<= 16 bytes per vertex): decode them in rounds of up to four
+	uint32_t block_mode;          // 1: block_offset is an INPUT (a block-offset sidecar: caller-provided, or kept from an earlier run):
+	                              // every block is walked on its own by one walker lane, which also checks that the block ends where
+	                              // the next one is said to start -- a stale sidecar is detected, never trusted (kStatusSidecar)
 };
+
+constexpr int32_t kStatusSidecar = -102; // = MOB200_ERR_SIDECAR (include/meshopt_b200.h)
 
 } // namespace mob200

@@ -222,7 +222,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		// look-back entries of the predecessor block.  Everything of one level is requested before any of it is used.
 		const uint32_t mi = i0 + lane;
 		const bool has = lane < kProducerBatch && mi < my_count;
-		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0;
+		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0, m_ready = 0;
 		uint32_t m_quanta = 0, m_len = 0; // rounds variant: decoder work quanta (32 items each) and staged bytes of the block
 		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
 		const uint32_t* boff = nullptr;
@@ -234,8 +234,6 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			const uint2 info = __ldg(T.ticket_info + t);
 			const uint32_t s = info.x, b = info.y;
 			const DevStream* d = T.streams + s;
-			const unsigned long long* progress = T.progress + s;
-			unsigned long long pv = ld_acquire_u64(progress);
 			src = d->src;
 			src_size = d->src_size;
 			const uint32_t vs = d->vertex_size;
@@ -249,15 +247,18 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			m_look = reinterpret_cast<unsigned long long>(T.lookback + (d->chan_base >> 2) + (uint64_t)b * (vs >> 2));
 			boff = T.block_offset + d->block_base + s + b;
 
-			// wait until the walker has published this block (back-off: a starved producer must not take issue
+			// wait until a walker has published this block (back-off: a starved producer must not take issue
 			// slots from the walker warps)
-			for (uint32_t ns = 32; (uint32_t)(pv >> 32) != T.epoch || ((uint32_t)pv & 0x7fffffffu) <= b;)
+			const uint32_t* ready = T.block_ready + d->block_base + b;
+			uint32_t rv = ld_acquire_u32(ready);
+			for (uint32_t ns = 32; (rv >> 2) != T.epoch;)
 			{
 				__nanosleep(ns);
 				ns = ns < 1024 ? ns * 2 : ns;
-				pv = ld_acquire_u64(progress);
+				rv = ld_acquire_u32(ready);
 			}
-			m_version = ((uint32_t)pv >> 31) & 1u;
+			m_version = (rv >> 1) & 1u;
+			m_ready = rv & 1u;
 		}
 		__syncwarp();
 
@@ -296,7 +297,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				if (nqj > 4)
 					m_ch_hi = ldg_u32_at(ch + 4, nqj - 4) & (nqj >= 8 ? 0xffffffffu : ((1u << (8 * (nqj - 4))) - 1u));
 			}
-			if (off != kInvalidOffset && end != kInvalidOffset)
+			if (m_ready && off != kInvalidOffset && end != kInvalidOffset)
 			{
 				m_valid = 1;
 				m_tail = reinterpret_cast<unsigned long long>(tail);
@@ -325,9 +326,14 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		// Rounds variant: the members of a round are all staged (slot, ring piece, TMA) before the carry of any of them is
 		// resolved -- the decoders start a round when every member has landed, and a carry may depend on a block that
 		// another unit decodes in a round of the same age, so a copy that waited for a carry could close a cycle.
+		// Plain form: the carry of block j is resolved after block j + 1 has been staged (a carry may have to wait for
+		// blocks that other units are still unpacking -- in block mode the predecessor is the ticket right before this
+		// one -- and the decoders should find their next block staged when it arrives).
 		uint32_t members = 1, g = 0, pass = 0;
-		for (uint32_t j0 = 0; j0 < in_batch;)
+		uint32_t js = 0, jc = 0; // plain form: next block to stage / to resolve the carry of
+		for (uint32_t j0 = 0; kRounds ? j0 < in_batch : jc < in_batch;)
 		{
+			const bool plain_stage = !kRounds && js < in_batch && js <= jc + 1;
 			if (kRounds && pass == 0 && g == 0)
 			{
 				// a block of at most two work quanta is joined by the following blocks of this batch as long as the round
@@ -353,9 +359,9 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 					}
 				}
 			}
-			const uint32_t j = j0 + g;
+			const uint32_t j = kRounds ? j0 + g : (plain_stage ? js : jc);
 			const uint32_t round_members = g == 0 ? members : 0u;
-			const bool do_stage = !kRounds || pass == 0, do_carry = !kRounds || pass == 1;
+			const bool do_stage = kRounds ? pass == 0 : plain_stage, do_carry = kRounds ? pass == 1 : !plain_stage;
 			const uint32_t i = i0 + j;
 			const uint32_t slot = i & (kSlots - 1);
 			SlotData& S = slots[slot];
@@ -471,6 +477,14 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 							S.P.round_members = round_members;
 						mbar_arrive(full + slot);
 					}
+					if (T.block_mode)
+					{
+						// block mode: later blocks of the stream may still be decodable (their output is garbage, as the
+						// reference allows for a rejected stream) and must not wait for this block's look-back entries
+						unsigned long long* look = reinterpret_cast<unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
+						for (uint32_t q = lane; q < nq; q += 32)
+							st_volatile_u64(look + q, ((unsigned long long)((T.epoch << 2) | 2u)) << 32);
+					}
 					__syncwarp();
 				}
 
@@ -502,7 +516,57 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 							S.carry[q0 + 3] = (uint32_t)pre3;
 					}
 				}
-				if (valid && !carry_done)
+				if (valid && !carry_done && b > 0 && nq <= 32)
+				{
+					// Decoupled look-back, 32 / nqp predecessors per step (nqp = nq rounded up to a power of two): lane =
+					// (predecessor pj, 4-byte lane q).  Per q the lanes consume the leading run of published predecessors up
+					// to the first inclusive prefix (state 2), combine their values with a butterfly over pj, and go on
+					// behind that run until a prefix has been met.  (Block 0 of a stream only ever publishes a prefix, so
+					// the walk never steps below it.)
+					const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
+					const uint32_t nqp = nq <= 1 ? 1u : (nq <= 2 ? 2u : (nq <= 4 ? 4u : (nq <= 8 ? 8u : (nq <= 16 ? 16u : 32u))));
+					const uint32_t q = lane & (nqp - 1u), pj = lane / nqp;
+					// bit pj * nqp for every predecessor slot of a step
+					const uint32_t pattern = nqp == 1 ? 0xffffffffu : (nqp == 2 ? 0x55555555u : (nqp == 4 ? 0x11111111u : (nqp == 8 ? 0x01010101u : (nqp == 16 ? 0x00010001u : 1u))));
+					const bool qon = q < nq;
+					const uint32_t Hq = lane_mask(qon ? S.channels[q] : 0u);
+					const uint32_t want_epoch = T.epoch & 0x3fffffffu;
+					bool done = !qon;
+					uint32_t acc = 0, dist = 1;
+					while (!__all_sync(0xffffffffu, done))
+					{
+						const bool here = !done && dist + pj <= b;
+						unsigned long long e = 0;
+						if (here)
+							e = ld_volatile_u64(look + q - (size_t)(dist + pj) * nq);
+						const uint32_t flag = (uint32_t)(e >> 32);
+						const uint32_t state = here ? ((flag >> 2) == want_epoch ? (flag & 3u) : 0u) : 2u; // (beyond block 0: never reached)
+						const uint32_t rmask = (__ballot_sync(0xffffffffu, state != 0) >> q) & pattern;
+						const uint32_t pmask = (__ballot_sync(0xffffffffu, state == 2) >> q) & pattern;
+						const uint32_t nr = ~rmask & pattern;                        // predecessors that have not published yet
+						const uint32_t below = nr ? ((nr & (0u - nr)) - 1u) : 0xffffffffu; // ... and everything nearer than the first of them
+						const uint32_t fp = (pmask & below) & (0u - (pmask & below)); // nearest inclusive prefix inside that run
+						uint32_t consume = below & pattern;
+						if (fp)
+							consume &= (fp << 1) - 1u;
+						uint32_t v = (!done && ((consume >> (pj * nqp)) & 1u)) ? (uint32_t)e : 0u;
+						for (uint32_t st = nqp; st < 32; st <<= 1)
+							v = lane_combine(v, __shfl_xor_sync(0xffffffffu, v, st), Hq);
+						if (!done)
+						{
+							acc = lane_combine(acc, v, Hq);
+							if (fp)
+								done = true;
+							else
+								dist += __popc(consume);
+							if (consume == 0)
+								__nanosleep(100);
+						}
+					}
+					if (qon && pj == 0)
+						S.carry[q] = acc;
+				}
+				else if (valid && !carry_done)
 				{
 					const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
 					for (uint32_t q = lane; q < nq; q += 32)
@@ -543,7 +607,12 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			} // do_carry
 
 			if (!kRounds)
-				++j0;
+			{
+				if (plain_stage)
+					++js;
+				else
+					++jc;
+			}
 			else if (++g == members)
 			{
 				g = 0;

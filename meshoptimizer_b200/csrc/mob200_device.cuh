@@ -94,6 +94,29 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 	asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// per-block hand-over word of DevTables::block_ready
+__device__ __forceinline__ uint32_t ready_word(uint32_t epoch, uint32_t version, bool decodable)
+{
+	return (epoch << 2) | ((version & 1u) << 1) | (decodable ? 1u : 0u);
+}
+
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 {
 	uint32_t v;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 		if (decode_on)
 			producer_main<kRounds>(T, smem, unit);
 	}
-	else if (walk_on && (g < 4 || T.n_streams > 4u * (kWideWalk ? 1u : 32u) * gridDim.x))
+	else if (walk_on && (g < 4 || (T.block_mode ? T.total_blocks : T.n_streams) > 4u * (kWideWalk ? 1u : 32u) * gridDim.x))
 	{
 		// (the fifth walker shares a scheduler with the first: it only runs when four per SM cannot take every
 		// stream in one round -- one walker per scheduler is 9% faster alone and 3% faster fused)

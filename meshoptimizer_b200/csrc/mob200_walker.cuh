@@ -17,7 +17,7 @@
 //   * byte-channels that are zero or literal in every lane (warp vote) are skipped without touching data.
 //
 // Output per block: its byte range (block_offset), one table row of 16 group entries per byte-channel
-// (group_table), a release store of the per-stream progress counter that hands the block to the
+// (group_table), a release store of the block's ready word that hands the block to the
 // producers, and at the end the reference return code of the stream (:1827-1869).
 #pragma once
 
@@ -369,12 +369,57 @@ __device__ __forceinline__ bool walk_block(WalkLane& L, WalkWarp& W, bool on, ui
 	return !bad;
 }
 
-// One pass of the walker warp over 32 streams (lane <-> stream base + lane).
-__device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base, uint32_t lane, uint32_t ring_smem)
+// Framing checks of one stream (reference src/vertexcodec.cpp:1827-1851, and the channel rule :1584-1585):
+// returns the reference code (0, -1, -2) and the codec version.
+__device__ __forceinline__ int walk_framing(const uint8_t* src, uint32_t size, uint32_t vs, uint32_t nblocks, uint32_t& version)
 {
-	const uint32_t s = base + lane;
-	const bool have = s < T.n_streams;
-	const DevStream* d = T.streams + (have ? s : 0);
+	int status = 0;
+	version = 0;
+	if (size < 1)
+		status = -2;
+	else
+	{
+		uint32_t h = __ldg(src);
+		version = h & 0x0f;
+		if ((h & 0xf0) != kMagic || version > 1)
+			status = -1;
+		else if (size - 1 < tail_padded(vs, version))
+			status = -2;
+	}
+	if (status == 0 && version != 0 && nblocks > 0)
+	{
+		// a channel byte with mode 3 makes the first block fail (:1584-1585)
+		const uint8_t* channels = src + size - vs / 4;
+		for (uint32_t q = 0; q < vs / 4; ++q)
+			if ((__ldg(channels + q) & 3u) == 3u)
+				status = -2;
+	}
+	if (status != 0)
+		version = 0;
+	return status;
+}
+
+// One pass of the walker warp over 32 lane jobs.
+//
+//   serial walk (DevTables::block_mode == 0): lane <-> stream base + lane, walked from byte 1 to its tail; every
+//     block's end offset goes to the block-offset table.
+//   block mode: lane <-> decode ticket base + lane = ONE block whose start comes from the block-offset table (a
+//     sidecar).  The lane walks that block -- group-table rows as usual -- and hands it to the producers only if the
+//     walk ends exactly where the table says the next block starts (the padded tail for the last block) and block 0
+//     starts at byte 1: the union of all verified blocks is then the chain the serial walk would have followed.
+//     Anything else marks the stream kStatusSidecar.
+__device__ void walk_group(const DevTables& T, WalkWarp& W, uint32_t base, uint32_t lane, uint32_t ring_smem)
+{
+	const bool bm = T.block_mode != 0;
+	const uint32_t job = base + lane;
+	const bool have = job < (bm ? T.total_blocks : T.n_streams);
+	uint32_t s = have ? job : 0, b_first = 0;
+	if (bm)
+	{
+		const uint2 info = have ? __ldg(T.ticket_info + job) : make_uint2(0u, 0u);
+		s = info.x, b_first = info.y;
+	}
+	const DevStream* d = T.streams + s;
 
 	WalkLane L;
 	L.src = d->src;
@@ -383,39 +428,24 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 	L.count = d->vertex_count;
 	L.bv = d->block_groups * kGroup;
 	L.nblocks = have ? d->nblocks : 0;
-	L.version = 0;
-	L.status = 0;
+	L.status = walk_framing(L.src, size, L.vs, L.nblocks, L.version);
 
 	uint32_t* boff = T.block_offset + d->block_base + s;
-	unsigned long long* progress = T.progress + s;
-	const unsigned long long tag = (unsigned long long)T.epoch << 32;
+	uint32_t* ready = T.block_ready + d->block_base;
 
-	// stream framing (reference src/vertexcodec.cpp:1827-1851)
-	if (size < 1)
-		L.status = -2;
-	else
+	uint32_t off = 1, want_end = 0;
+	if (bm && have && L.status == 0)
 	{
-		uint32_t h = __ldg(L.src);
-		L.version = h & 0x0f;
-		if ((h & 0xf0) != kMagic || L.version > 1)
-			L.status = -1;
-		else if (size - 1 < tail_padded(L.vs, L.version))
-			L.status = -2;
+		off = __ldcg(boff + b_first);
+		want_end = __ldcg(boff + b_first + 1);
+		const uint32_t body_end = size - tail_padded(L.vs, L.version); // (:1868) the blocks end where the padded tail starts
+		if (off < 1 || off > body_end || want_end < off || want_end > body_end || (b_first == 0 && off != 1) || (b_first + 1 == L.nblocks && want_end != body_end))
+			L.status = kStatusSidecar;
 	}
-	if (L.status == 0 && L.version != 0 && L.nblocks > 0)
-	{
-		// a channel byte with mode 3 makes the first block fail (:1584-1585)
-		const uint8_t* channels = L.src + size - L.vs / 4;
-		for (uint32_t q = 0; q < L.vs / 4; ++q)
-			if ((__ldg(channels + q) & 3u) == 3u)
-				L.status = -2;
-	}
-	if (L.status != 0)
-		L.version = 0;
 
 	L.rel0 = (uint32_t)(reinterpret_cast<uintptr_t>(L.src) & 15u);
 	L.org = L.src - L.rel0;
-	L.rel = L.rel0 + 1;
+	L.rel = L.rel0 + off;
 	L.rel_end = L.rel0 + size;
 	L.limit = (L.rel_end + 15u) & ~15u;
 	L.sbase = ring_smem | ((lane & 7u) << 4);
@@ -424,54 +454,76 @@ __device__ void walk_stream_group(const DevTables& T, WalkWarp& W, uint32_t base
 	L.prefetched = 0;
 
 	const bool framed = have && L.status == 0;
-	uint32_t done = 0; // blocks [0, done) are decodable
+	const uint32_t b_count = bm ? 1u : L.nblocks; // blocks this lane walks
+	uint32_t done = 0;                            // blocks [b_first, b_first + done) are decodable
 	bool alive = framed;
 	if (!framed)
-		L.limit = 0; // nothing is fetched for a stream that is not walked
+		L.limit = 0; // nothing is fetched for a job that is not walked
 	L.last = (L.limit + kWalkChunkBytes - 1) / kWalkChunkBytes;
-	if (framed && L.nblocks)
+	if (!bm && framed && L.nblocks)
 		boff[0] = 1;
 
-	const uint32_t max_blocks = __reduce_max_sync(0xffffffffu, alive ? L.nblocks : 0u);
-	for (uint32_t b = 0; b < max_blocks; ++b)
+	const uint32_t max_blocks = __reduce_max_sync(0xffffffffu, alive ? b_count : 0u);
+	for (uint32_t i = 0; i < max_blocks; ++i)
 	{
-		const bool on = alive && b < L.nblocks;
+		const uint32_t b = b_first + i;
+		const bool on = alive && i < b_count;
 		const uint32_t n = on ? min(L.bv, L.count - b * L.bv) : 16u;
 		const uint32_t vs_max = __reduce_max_sync(0xffffffffu, on ? L.vs : 0u);
 		uint16_t* rows = T.group_table + (d->chan_base + (uint64_t)b * L.vs) * 16;
 		const bool ok = walk_block(L, W, on, n, rows, vs_max, lane);
 		if (on)
 		{
-			if (ok)
+			if (ok && (!bm || L.rel - L.rel0 == want_end))
 			{
-				boff[b + 1] = L.rel - L.rel0;
-				done = b + 1;
-				st_release_u64(progress, tag | (L.version << 31) | done);
+				if (!bm)
+					boff[b + 1] = L.rel - L.rel0;
+				done = i + 1;
+				st_release_u32(ready + b, ready_word(T.epoch, L.version, true));
 			}
 			else
 			{
-				L.status = -2;
+				L.status = bm ? kStatusSidecar : -2;
 				alive = false;
 			}
 		}
 	}
-	// every copy into the rings has landed before the lanes move on to their next streams
+	// every copy into the rings has landed before the lanes move on to their next jobs
 	if (W.pending)
 		walk_wait(W);
 
 	if (have)
 	{
-		if (L.status == 0 && L.rel_end - L.rel != tail_padded(L.vs, L.version))
+		if (!bm && L.status == 0 && L.rel_end - L.rel != tail_padded(L.vs, L.version))
 			L.status = -3; // (:1868-1869) the blocks were decodable, the stream is still rejected
-		if (done < L.nblocks)
+		if (done < b_count)
 		{
 			// block `done` failed (or the framing did): its end offset and everything after it is invalid
-			for (uint32_t b = framed ? done + 1 : 0; b <= L.nblocks; ++b)
-				boff[b] = kInvalidOffset;
-			st_release_u64(progress, tag | L.nblocks); // nothing more will come: the producers skip the rest
+			if (!bm)
+				for (uint32_t b = framed ? done + 1 : 0; b <= L.nblocks; ++b)
+					boff[b] = kInvalidOffset;
+			for (uint32_t b = b_first + done; b < b_first + b_count; ++b)
+				st_release_u32(ready + b, ready_word(T.epoch, 0, false)); // nothing more will come: the producers skip the rest
 		}
-		T.status[d->caller_index] = L.status;
+		if (!bm || L.status != 0)
+			T.status[d->caller_index] = L.status; // (block mode: the status words are cleared before the launch)
 	}
+}
+
+// Block mode: streams without blocks (vertex_count 0) only have their framing checked; they follow the streams
+// with blocks in the sorted stream array.
+__device__ void walk_frame_group(const DevTables& T, uint32_t base, uint32_t lane)
+{
+	const uint32_t s = base + lane;
+	if (s >= T.n_streams)
+		return;
+	const DevStream* d = T.streams + s;
+	uint32_t version;
+	int status = walk_framing(d->src, d->src_size, d->vertex_size, 0, version);
+	if (status == 0 && d->src_size - 1 != tail_padded(d->vertex_size, version))
+		status = -3; // (:1868-1869)
+	if (status != 0)
+		T.status[d->caller_index] = status;
 }
 
 __device__ void walker_main(const DevTables& T, uint8_t* region)
@@ -491,15 +543,26 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 	walk_lut_init(region + kWalkSmemLut, lane);
 	__syncwarp();
 
+	// block mode: tickets [0, total_blocks) in groups of 32, then the streams that have no blocks
+	const uint32_t ticket_span = (T.total_blocks + 31u) & ~31u;
 	for (;;)
 	{
 		uint32_t base = 0;
 		if (lane == 0)
 			base = atomicAdd(T.counters + 1, 32u);
 		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= T.n_streams)
-			break;
-		walk_stream_group(T, W, base, lane, ring_smem);
+		if (T.block_mode && base >= ticket_span)
+		{
+			if (T.n_with_blocks + (base - ticket_span) >= T.n_streams)
+				break;
+			walk_frame_group(T, T.n_with_blocks + (base - ticket_span), lane);
+		}
+		else
+		{
+			if (!T.block_mode && base >= T.n_streams)
+				break;
+			walk_group(T, W, base, lane, ring_smem);
+		}
 		__syncwarp();
 	}
 #ifdef MOB200_DEBUG_COUNTERS

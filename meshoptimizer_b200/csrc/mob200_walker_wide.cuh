@@ -17,7 +17,7 @@
 //      the 24-byte rule is tested once per channel, outside the chain.
 //
 // Outputs are identical to the lane-per-stream walker (mob200_walker.cuh): block byte ranges, one table row
-// of 16 group entries per byte-channel, a release store of the stream's progress per block, and the
+// of 16 group entries per byte-channel, a release store of the block's ready word, and the
 // reference return code (src/vertexcodec.cpp:1827-1869).
 #pragma once
 
@@ -143,8 +143,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 	const uint32_t nblocks = d->nblocks;
 
 	uint32_t* boff = T.block_offset + d->block_base + s;
-	unsigned long long* progress = T.progress + s;
-	const unsigned long long tag = (unsigned long long)T.epoch << 32;
+	uint32_t* ready = T.block_ready + d->block_base;
 	const uint32_t tab_base = smem_base + kWideRingBytes;
 
 	int status = 0;
@@ -175,6 +174,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 	const uint32_t rel_end = rel0 + size;
 	uint32_t rel = rel0 + 1;
 	uint32_t done = 0;
+	uint32_t published_blocks = 0;
 	const bool framed = status == 0;
 
 	if (framed && nblocks)
@@ -188,6 +188,7 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 		if (lane == 0)
 			boff[0] = 1;
 		const uint32_t publish_every = vs <= 8 ? 4u : (vs <= 16 ? 2u : 1u);
+		uint32_t published = 0; // blocks [0, published) have been handed to the producers
 		for (uint32_t b = 0; b < nblocks && status == 0; ++b)
 		{
 			const uint32_t n = min(bv, count - b * bv);
@@ -357,10 +358,16 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 			// the ~850 per byte-channel of a block that has only 4 ... 16 of them)
 			if (lane == 0 && ((done & (publish_every - 1u)) == 0 || done == nblocks))
 			{
-				// (the table rows were written by other lanes before the __syncwarp above: the release below is a
-				// fence + store and cumulative over what this lane has synchronised with, so no fence of its own is
-				// needed here -- a second MEMBAR.GPU per block was a fifth of the walk of a 4-byte-vertex stream)
-				st_release_u64(progress, tag | (version << 31) | done);
+				// (the table rows were written by other lanes before the __syncwarp above: the
+				// fence is cumulative over what this lane has synchronised with, and every strong store that follows it in
+				// program order is a release: one MEMBAR.GPU per group of blocks -- a second one per block was a fifth of
+				// the walk of a 4-byte-vertex stream)
+				const uint32_t word = ready_word(T.epoch, version, true);
+				asm volatile("fence.acq_rel.gpu;" ::: "memory");
+				for (uint32_t p = published; p < done; ++p)
+					st_volatile_u32(ready + p, word);
+				published = done;
+				published_blocks = done;
 			}
 		}
 		asm volatile("cp.async.wait_all;" ::: "memory");
@@ -376,7 +383,11 @@ __device__ void walk_stream_wide(const DevTables& T, uint32_t s, uint32_t lane, 
 		{
 			for (uint32_t b = framed ? done + 1 : 0; b <= nblocks; ++b)
 				boff[b] = kInvalidOffset;
-			st_release_u64(progress, tag | ((version & 1u) << 31) | nblocks); // (blocks walked before the failure may still be waiting for their release)
+			// blocks walked before the failure may still be waiting for their release; the rest is not decodable
+			__threadfence();
+			for (uint32_t b = 0; b < nblocks; ++b)
+				if (b >= done || b >= published_blocks)
+					st_volatile_u32(ready + b, ready_word(T.epoch, version, b < done));
 		}
 		T.status[d->caller_index] = status;
 	}

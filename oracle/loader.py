@@ -182,6 +182,18 @@ class _Lib:
         best = self.lib.harness_decode_mt(arr, n, threads, passes, times)
         return best, list(times), [o[: c * v] for o, (_, c, v, _) in zip(outs, streams)], [arr[i].status for i in range(n)]
 
+    def block_offsets(self, vertex_count: int, vertex_size: int, data):
+        """(return code, block-offset table uint32[nblocks + 1]) -- port only (the reference has no such entry point)"""
+        f = self.lib.oracle_vertexBlockOffsets
+        f.restype = c_int
+        f.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
+        src = _u8(data)
+        bv = min(256, (8192 // vertex_size) & ~15)
+        nb = (vertex_count + bv - 1) // bv
+        out = np.zeros(nb + 1 if nb else 1, dtype=np.uint32)
+        rc = f(out.ctypes.data, vertex_count, vertex_size, src.ctypes.data if src.size else None, src.size)
+        return int(rc), out[: nb + 1 if nb else 0]
+
     def hw_threads(self) -> int:
         return int(self.lib.harness_hw_threads())
 

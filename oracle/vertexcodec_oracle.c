@@ -287,3 +287,46 @@ ORACLE_API int oracle_decodeVertexBuffer(void* destination, size_t vertex_count,
 
 	return buffer_size - pos == tail_padded ? 0 : -3;
 }
+
+/* Block-offset table of a stream ("sidecar", include/meshopt_b200.h section 2b): offsets[b] = byte offset of block
+ * b for b < nblocks, offsets[nblocks] = end of the last block.  Walks exactly as oracle_decodeVertexBuffer does
+ * (the blocks are decoded into scratch).  Returns the decoder's return code; `offsets` needs nblocks + 1 entries. */
+ORACLE_API int oracle_vertexBlockOffsets(unsigned int* offsets, size_t vertex_count, size_t vertex_size, const unsigned char* buffer, size_t buffer_size)
+{
+	if (vertex_size == 0 || vertex_size > 256 || vertex_size % 4 != 0)
+		return -4;
+	if (buffer_size < 1)
+		return -2;
+	if ((buffer[0] & 0xf0) != MAGIC)
+		return -1;
+	int version = buffer[0] & 0x0f;
+	if (version > MAX_VERSION)
+		return -1;
+
+	size_t tail = vertex_size + (version == 0 ? 0 : vertex_size / 4);
+	size_t tail_min = version == 0 ? TAIL_MIN_V0 : TAIL_MIN_V1;
+	size_t tail_padded = tail < tail_min ? tail_min : tail;
+	if (buffer_size - 1 < tail_padded)
+		return -2;
+
+	const uint8_t* tail_ptr = buffer + buffer_size - tail;
+	uint8_t prev[256];
+	memcpy(prev, tail_ptr, vertex_size);
+	const uint8_t* channels = version == 0 ? NULL : tail_ptr + vertex_size;
+
+	static __thread uint8_t scratch[BLOCK_BYTES];
+	size_t block = oracle_block_size(vertex_size);
+	size_t pos = 1, b = 0;
+	for (size_t first = 0; first < vertex_count; first += block, ++b)
+	{
+		size_t n = vertex_count - first < block ? vertex_count - first : block;
+		offsets[b] = (unsigned int)pos;
+		size_t used = decode_block(buffer + pos, buffer_size - pos, scratch, n, vertex_size, prev, channels, version);
+		if (used == (size_t)-1)
+			return -2;
+		pos += used;
+	}
+	if (vertex_count)
+		offsets[b] = (unsigned int)pos;
+	return buffer_size - pos == tail_padded ? 0 : -3;
+}

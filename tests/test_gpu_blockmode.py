@@ -1,0 +1,187 @@
+"""-m gpu: block mode -- every block walked by its own lane from a block-offset sidecar (include/meshopt_b200.h
+section 2b; the serial loop it replaces: reference src/vertexcodec.cpp:1857-1866).
+
+* a plan that has run once decodes again block-parallel, bit-exact (monolithic, segmented, filtered, tiny streams);
+* exported sidecars equal the CPU checker's block offsets, and a fresh plan created WITH them decodes without
+  ever running the serial walk;
+* a sidecar is never trusted: a shifted entry, a sidecar of another stream, input bytes changed after the walk
+  and random garbage are all rejected with MOB200_ERR_SIDECAR (no hang, no write outside the outputs).
+"""
+import numpy as np
+import pytest
+
+from oracle import loader, workloads
+from tests.gpu_util import device_run, first_mismatch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import meshoptimizer_b200 as m
+
+    m.lib()
+    return m
+
+
+def _expected(w):
+    if w.source is not None and int(w.filters.max()) == 0:
+        outs, o = [], 0
+        for i in range(w.n):
+            nbytes = int(w.counts[i]) * int(w.vertex_sizes[i])
+            outs.append(w.source[o : o + nbytes])
+            o += nbytes
+        return outs
+    return workloads.expected_outputs(w)
+
+
+def _same(w, outs, want):
+    for i, (a, b) in enumerate(zip(outs, want)):
+        if int(w.vertex_sizes[i]) == 4 and int(w.filters[i]) in (1, 4):
+            d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+            if int(np.minimum(d, 256 - d).max(initial=0)) > 1:
+                return f"stream {i}: more than 1 LSB apart"
+        else:
+            m = first_mismatch(a, b)
+            if m is not None:
+                return f"stream {i}: {m}"
+    return None
+
+
+WORKLOADS = {
+    "c2_mono_256k": lambda: workloads.c2(total=1 << 18, seg=None),
+    "c2_mono_ragged": lambda: workloads.c2(total=100_003, seg=None),
+    "c2_seg_4096": lambda: workloads.c2(total=1 << 19, seg=1 << 12),
+    "c2_l3_xor": lambda: workloads.c2(total=1 << 17, seg=1 << 15, level=3),
+    "c2_v0": lambda: workloads.c2(total=1 << 17, seg=None, level=0, version=0),
+    "c1a_v0": lambda: workloads.c1a(version=0, level=0, side=200),
+    "c1b_v1": lambda: workloads.c1b(version=1, count=1 << 16),
+    "c3_oct8": lambda: workloads.c3("oct8", count=1 << 17, seg=1 << 15),
+    "c3_quat12_v0": lambda: workloads.c3("quat12", count=70_000, seg=None, version=0, level=0),
+    "c3_exp15": lambda: workloads.c3("exp15", count=1 << 16, seg=1 << 14),
+    "c4": lambda: workloads.c4(3000),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WORKLOADS))
+def test_block_mode_reuses_offsets(mb, name):
+    w = WORKLOADS[name]()
+    want = _expected(w)
+    outs, status, plan, guard = device_run(w, runs=1, block_runs=2)
+    assert plan.has_offsets
+    assert (status == 0).all(), status[status != 0][:8]
+    assert guard
+    assert _same(w, outs, want) is None, _same(w, outs, want)
+
+
+@pytest.mark.parametrize("name", ["c2_mono_256k", "c2_seg_4096", "c1a_v0", "c3_oct8", "c4"])
+def test_sidecar_export_import(mb, name):
+    w = WORKLOADS[name]()
+    want = _expected(w)
+    outs, status, plan, guard = device_run(w, runs=1)
+    assert (status == 0).all()
+    port = loader.port()
+    sidecars = []
+    for i in range(w.n):
+        sc = plan.export_sidecar(i, int(w.counts[i]), int(w.vertex_sizes[i]))
+        rc, off = port.block_offsets(int(w.counts[i]), int(w.vertex_sizes[i]), w.stream(i))
+        assert rc == 0 and np.array_equal(sc, off), f"stream {i}: exported sidecar differs from the CPU walk"
+        sidecars.append(sc.copy())
+    del plan
+    # a fresh plan that only ever runs in block mode
+    outs2, status2, plan2, guard2 = device_run(w, runs=0, sidecars=sidecars, block_runs=1)
+    assert (status2 == 0).all() and guard2
+    assert _same(w, outs2, want) is None
+
+
+def _sidecars(w):
+    port = loader.port()
+    out = []
+    for i in range(w.n):
+        rc, off = port.block_offsets(int(w.counts[i]), int(w.vertex_sizes[i]), w.stream(i))
+        assert rc == 0
+        out.append(off.copy())
+    return out
+
+
+def test_stale_sidecar_is_rejected(mb):
+    w = workloads.c2(total=1 << 17, seg=1 << 14)  # 8 streams x 64 blocks
+    want = _expected(w)
+    sc = _sidecars(w)
+    bad = [s.copy() for s in sc]
+    bad[1][10] += 1             # one block start off by one
+    bad[3] = sc[4].copy()       # another stream's table (same length, different data)
+    bad[5][-1] -= 1             # the end of the last block
+    bad[6][0] = 2               # block 0 must start at byte 1
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=bad, block_runs=1)
+    assert guard
+    assert list(status) == [0, mb.ERR_SIDECAR, 0, mb.ERR_SIDECAR, 0, mb.ERR_SIDECAR, mb.ERR_SIDECAR, 0], status
+    for i in (0, 2, 4, 7):
+        assert np.array_equal(outs[i], want[i])
+    # decoding again without the sidecar gives the reference result for every stream
+    outs, status, plan, guard = device_run(w, runs=1)
+    assert (status == 0).all() and _same(w, outs, want) is None
+
+
+def test_changed_input_is_caught(mb):
+    """offsets kept from a walk of other bytes: the block that no longer ends where the table says is rejected"""
+    import torch
+
+    w = workloads.c2(total=1 << 16, seg=None)
+    sc = _sidecars(w)
+    blob = w.blob.copy()
+    # clear the selector byte of a bit-packed channel header in block 3: its groups change width, the block shrinks
+    o = int(w.offsets[0]) + int(sc[0][3]) + 8  # 8 control bytes, then channel 0's header
+    assert blob[o] != 0
+    blob[o] = 0
+    rc, _ = loader.ref().decode_vertex_buffer(int(w.counts[0]), 32, blob[int(w.offsets[0]) : int(w.offsets[0]) + int(w.sizes[0])]) if loader.have_ref() else (-1, None)
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=sc, block_runs=1, blob_override=blob)
+    assert guard and status[0] == mb.ERR_SIDECAR
+    if loader.have_ref():
+        assert rc != 0  # (the reference rejects the modified stream as well)
+
+
+def test_garbage_sidecars_are_safe(mb):
+    rng = np.random.default_rng(5)
+    w = workloads.c2(total=1 << 16, seg=1 << 12)
+    sc = _sidecars(w)
+    bad = []
+    for i, s in enumerate(sc):
+        g = s.copy()
+        kind = i % 4
+        if kind == 0:
+            g[:] = rng.integers(0, 1 << 32, size=g.size, dtype=np.uint64).astype(np.uint32)
+        elif kind == 1:
+            g[:] = rng.integers(0, int(w.sizes[i]) + 64, size=g.size).astype(np.uint32)
+        elif kind == 2:
+            g[:] = np.sort(rng.integers(1, int(w.sizes[i]), size=g.size)).astype(np.uint32)
+            g[0] = 1
+        else:
+            g[1:-1] = g[1:-1][::-1]
+        bad.append(g)
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=bad, block_runs=2)
+    assert guard
+    assert (status == mb.ERR_SIDECAR).all(), status
+
+
+def test_block_mode_needs_offsets(mb):
+    w = workloads.c2(total=4096, seg=None)
+    import torch
+
+    with pytest.raises(RuntimeError):
+        device_run(w, runs=0, block_runs=1)
+
+
+def test_block_mode_error_streams(mb, checker):
+    """framing errors keep their reference codes in block mode; empty streams are checked too"""
+    w = workloads.c2(total=1 << 14, seg=1 << 12)
+    sc = _sidecars(w)
+    blob = w.blob.copy()
+    blob[int(w.offsets[1])] = 0x55       # bad magic -> -1
+    blob[int(w.offsets[2])] = 0xA2       # version 2 -> -1
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=sc, block_runs=1, blob_override=blob)
+    assert guard and list(status) == [0, -1, -1, 0]

@@ -30,7 +30,7 @@ for _ in range(3):
     plan.run(stream)
     torch.cuda.synchronize()
     d = plan.debug_counters(reset=True)
-    t = plan.timing_history(1)[-1]["total_ms"]
+    t = plan.timing_history(1)[-1]
     mhz = 1965.0
     print(f"decoder failed polls (cumulative, warp level) {d['walker_hard_waits']} |", end=" ")
     print(f"kernel {t:.3f} ms | walkers: mean end {d['r13']/max(1,(n+31)//32)/mhz/1e3:.3f} ms, last end {d['r15']/mhz/1e3:.3f} ms | decoders: last end {d['r14']/mhz/1e3:.3f} ms (cycles at {mhz:.0f} MHz)")
