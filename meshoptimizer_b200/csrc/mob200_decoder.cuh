@@ -309,12 +309,12 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				m_lo = lo;
 				m_enc = (uint32_t)(hi - lo);
 				m_shift = (uint32_t)(a0 - lo);
+				m_len = m_enc + (vs <= kRowsInRingMaxVs ? 32u * vs : 0u);
 				if (kRounds)
 				{
 					const uint32_t groups_j = (m_n + kGroup - 1) / kGroup;
 					const uint32_t gshift_j = groups_j > 8 ? 4u : (groups_j > 4 ? 3u : (groups_j > 2 ? 2u : (groups_j > 1 ? 1u : 0u)));
 					m_quanta = (((vs >> 2) << gshift_j) + 31u) >> 5;
-					m_len = m_enc + (vs <= kRowsInRingMaxVs ? 32u * vs : 0u);
 				}
 			}
 		}
@@ -333,7 +333,16 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		uint32_t js = 0, jc = 0; // plain form: next block to stage / to resolve the carry of
 		for (uint32_t j0 = 0; kRounds ? j0 < in_batch : jc < in_batch;)
 		{
-			const bool plain_stage = !kRounds && js < in_batch && js <= jc + 1;
+			bool plain_stage = !kRounds && js < in_batch && js == jc;
+			if (!kRounds && js < in_batch && js == jc + 1)
+			{
+				// one block ahead of the carry -- but only if its ring piece can be had without waiting for block jc itself
+				// (whose decoders wait for the carry this warp has not resolved yet): with jc the only live piece the
+				// allocator below takes `head` if the piece fits behind it, else offset 0 if it fits in front of it
+				const uint32_t lens = __shfl_sync(0xffffffffu, m_len, js);
+				const uint32_t slot_c = (i0 + jc) & (kSlots - 1);
+				plain_stage = ring_len[slot_c] == 0 || head + lens <= kStageRingBytes || lens < ring_start[slot_c];
+			}
 			if (kRounds && pass == 0 && g == 0)
 			{
 				// a block of at most two work quanta is joined by the following blocks of this batch as long as the round
