@@ -155,8 +155,14 @@ MESHOPTIMIZER_API int mob200_decode_batch_device(mob200_Context* ctx, mob200_Str
 /* Same contract with HOST pointers in src/dst: compressed bytes go host->device, decoded (and
  * filtered) vertices come device->host, pipelined in chunks over several CUDA streams.  Pinned
  * (page-locked) caller buffers are transferred in place, pageable ones through pinned staging.
- * Synchronous; fills streams[i].status; returns the number of failed streams or MOB200_ERR_*. */
+ * Synchronous; fills streams[i].status (a stream with illegal arguments gets MOB200_ERR_ARGUMENT and the
+ * rest of the batch is still decoded); returns the number of failed streams or MOB200_ERR_*.  Nothing is
+ * left in flight when the call returns, also on failure. */
 MESHOPTIMIZER_API int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* streams, size_t n);
+
+/* mob200_decode_batch_host with one host block-offset sidecar per stream (section 2b; NULL array = none): chunks
+ * whose streams all carry one are decoded in block mode. */
+MESHOPTIMIZER_API int mob200_decode_batch_host_sidecar(mob200_Context* ctx, mob200_Stream* streams, size_t n, const unsigned int* const* sidecars);
 
 /* In-place decode filter on a DEVICE buffer of count elements (asynchronous on cuda_stream).
  * filter is enum mob200_Filter (not NONE); stride rules as the reference asserts them. */
@@ -284,17 +290,22 @@ typedef struct mob200_GltfInfo
 } mob200_GltfInfo;
 
 /* Find the compressed bufferViews of a .glb container or of bare .gltf JSON text.  Writes up to view_capacity
- * views and up to buffer_capacity byteLength values of buffers[] (either array may be NULL).  Host only, no
- * device work.  Returns 0, or MOB200_ERR_ARGUMENT for a malformed container / JSON. */
+ * views and up to buffer_capacity byteLength values of buffers[] (either array may be NULL).  Views that break the
+ * extension's rules, name a buffer the asset does not have, or (when buffer_sizes is given) reach outside their
+ * buffers are returned with status MOB200_ERR_ARGUMENT.  JSON nested deeper than 64 levels is rejected.  Host only,
+ * no device work.  Returns 0, or MOB200_ERR_ARGUMENT for a malformed container / JSON. */
 MESHOPTIMIZER_API int mob200_gltf_scan(const void* data, size_t size, mob200_GltfView* views, size_t view_capacity, size_t* buffer_sizes, size_t buffer_capacity, mob200_GltfInfo* info);
 
-/* Decode all views in one batch per codec family.  buffers[i] / outputs[i]: where buffers[i] of the asset is
- * loaded / where decompressed views that belong to buffers[i] go (NULL entries make the views that need them
- * fail with MOB200_ERR_ARGUMENT); buffer_sizes (optional) bounds the source ranges.  Host pointers, synchronous.
- * Returns the number of views whose status is non-zero, or MOB200_ERR_*. */
-MESHOPTIMIZER_API int mob200_gltf_decode_host(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs);
+/* Decode all views in one batch per codec family.  The asset has buffer_count buffers; buffers[i] (buffer_sizes[i]
+ * bytes) is where buffers[i] of the asset is loaded, outputs[i] (output_sizes[i] bytes) is where decompressed views
+ * that belong to buffers[i] go.  All four arrays have buffer_count entries and are mandatory; NULL pointers in
+ * buffers[] / outputs[] make the views that need them fail.  Every view is checked against these bounds before
+ * anything is read or written: a view that names a buffer >= buffer_count, or whose source or destination range
+ * does not lie inside its buffer, gets MOB200_ERR_ARGUMENT (views come from untrusted JSON).  Host pointers,
+ * synchronous.  Returns the number of views whose status is non-zero, or MOB200_ERR_*. */
+MESHOPTIMIZER_API int mob200_gltf_decode_host(mob200_Context* ctx, mob200_GltfView* views, size_t n, size_t buffer_count, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs, const size_t* output_sizes);
 /* Same with device pointers in buffers[] / outputs[]. */
-MESHOPTIMIZER_API int mob200_gltf_decode_device(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* device_buffers, const size_t* buffer_sizes, void* const* device_outputs, void* cuda_stream);
+MESHOPTIMIZER_API int mob200_gltf_decode_device(mob200_Context* ctx, mob200_GltfView* views, size_t n, size_t buffer_count, const void* const* device_buffers, const size_t* buffer_sizes, void* const* device_outputs, const size_t* output_sizes, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -105,7 +105,7 @@ EXPORTS = [
     "meshopt_decodeFilterOct", "meshopt_decodeFilterQuat", "meshopt_decodeFilterExp", "meshopt_decodeFilterColor",
     "mob200_context_create", "mob200_context_destroy", "mob200_plan_create", "mob200_plan_destroy",
     "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
-    "mob200_decode_batch_host", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
+    "mob200_decode_batch_host", "mob200_decode_batch_host_sidecar", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
     "mob200_plan_last_timing", "mob200_plan_timing_history", "mob200_plan_debug_counters", "mob200_plan_create_ms",
     "mob200_sidecar_entries", "mob200_plan_create_sidecar", "mob200_plan_run_ex", "mob200_plan_has_offsets", "mob200_plan_export_sidecar",
     "meshopt_decodeIndexBuffer", "meshopt_decodeIndexVersion", "meshopt_decodeIndexSequence",
@@ -199,9 +199,11 @@ def lib() -> ctypes.CDLL:
     L.mob200_gltf_scan.restype = c_int
     L.mob200_gltf_scan.argtypes = [c_void_p, c_size_t, POINTER(GltfView), c_size_t, POINTER(c_size_t), c_size_t, POINTER(GltfInfo)]
     L.mob200_gltf_decode_host.restype = c_int
-    L.mob200_gltf_decode_host.argtypes = [c_void_p, POINTER(GltfView), c_size_t, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p)]
+    L.mob200_gltf_decode_host.argtypes = [c_void_p, POINTER(GltfView), c_size_t, c_size_t, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), POINTER(c_size_t)]
     L.mob200_gltf_decode_device.restype = c_int
-    L.mob200_gltf_decode_device.argtypes = [c_void_p, POINTER(GltfView), c_size_t, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), c_void_p]
+    L.mob200_gltf_decode_device.argtypes = [c_void_p, POINTER(GltfView), c_size_t, c_size_t, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p), POINTER(c_size_t), c_void_p]
+    L.mob200_decode_batch_host_sidecar.restype = c_int
+    L.mob200_decode_batch_host_sidecar.argtypes = [c_void_p, POINTER(Stream), c_size_t, POINTER(c_void_p)]
     _LIB = L
     return L
 
@@ -624,12 +626,14 @@ def gltf_decode_host(data, external_buffers: Optional[dict] = None, ctx: Optiona
             lens[i] = b.size
     outputs = {}
     outs = (c_void_p * nb)()
+    out_lens = (c_size_t * nb)()
     for k in range(n):
         d = views[k].dst_buffer
         if d < info.buffer_count and d not in outputs:
             outputs[d] = np.zeros(max(sizes[d], 1), dtype=np.uint8)
             outs[d] = outputs[d].ctypes.data
-    rc = lib().mob200_gltf_decode_host(ctx.handle, views, n, bufs, lens, outs)
+            out_lens[d] = sizes[d]
+    rc = lib().mob200_gltf_decode_host(ctx.handle, views, n, info.buffer_count, bufs, lens, outs, out_lens)
     if rc < 0:
         raise RuntimeError(f"mob200_gltf_decode_host failed ({rc})")
     return outputs, views, info

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -320,7 +321,7 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	{
 		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
 	}
-	std::vector<uint32_t> side; // (must outlive the asynchronous copy: synchronised below)
+	std::vector<uint32_t> side;
 	if (sidecars)
 	{
 		// block-offset sidecars: stream i (sorted) owns entries [block_base + i, block_base + i + nblocks] of the table;
@@ -341,8 +342,8 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 		}
 		if (all && total_blocks)
 		{
+			// (pageable source: like the descriptor uploads above, the call returns once the bytes are staged)
 			ok = ok && cudaMemcpyAsync(base + off_boff, side.data(), side.size() * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
-			ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
 			plan->have_offsets = true;
 		}
 	}
@@ -669,7 +670,23 @@ static size_t run_device_offset(const HostRun& r, uintptr_t p)
 	return r.dev_base + (r.begin & 15) + (size_t)(p - r.begin);
 }
 
+static bool stream_args_ok(const mob200_Stream& s)
+{
+	if (s.vertex_size == 0 || s.vertex_size > 256 || s.vertex_size % 4 != 0) // reference asserts, src/vertexcodec.cpp:1803-1804
+		return false;
+	if (s.vertex_count >= 0xffffffffull || s.src_size >= 0xffffffffull || !filter_ok(s.filter, s.vertex_size))
+		return false;
+	if (s.vertex_count && !s.dst)
+		return false;
+	return true;
+}
+
 extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* streams, size_t n)
+{
+	return mob200_decode_batch_host_sidecar(ctx, streams, n, nullptr);
+}
+
+extern "C" int mob200_decode_batch_host_sidecar(mob200_Context* ctx, mob200_Stream* streams, size_t n, const unsigned int* const* sidecars)
 {
 	if (!ctx || (n && !streams))
 		return MOB200_ERR_ARGUMENT;
@@ -679,37 +696,44 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 	if (n == 0)
 		return 0;
 
+	// Every stream is validated up front: one with illegal arguments gets MOB200_ERR_ARGUMENT as its own status and is
+	// replaced by an empty placeholder, the rest of the batch is decoded.
+	std::vector<uint8_t> skipped(n, 0);
+	std::vector<mob200_Stream> host(streams, streams + n);
 	for (size_t i = 0; i < n; ++i)
-	{
-		const mob200_Stream& s = streams[i];
-		if (s.vertex_size == 0 || s.vertex_size > 256 || s.vertex_size % 4 != 0)
-			return MOB200_ERR_ARGUMENT;
-		if (s.vertex_count && !s.dst)
-			return MOB200_ERR_ARGUMENT;
-	}
+		if (!stream_args_ok(streams[i]))
+		{
+			skipped[i] = 1;
+			host[i].src = nullptr;
+			host[i].src_size = 0;
+			host[i].dst = nullptr;
+			host[i].vertex_count = 0;
+			host[i].vertex_size = 4;
+			host[i].filter = MOB200_FILTER_NONE;
+		}
 
 	// host ranges -> runs -> device layout
 	std::vector<HostRun> in_runs, out_runs;
 	std::vector<size_t> in_run_of, out_run_of;
 	size_t in_total = 0, out_total = 0;
 	build_runs(n, [&](size_t i, uintptr_t& p, size_t& len) {
-		p = reinterpret_cast<uintptr_t>(streams[i].src);
-		len = streams[i].src ? streams[i].src_size : 0;
+		p = reinterpret_cast<uintptr_t>(host[i].src);
+		len = host[i].src ? host[i].src_size : 0;
 	}, 15, in_runs, in_run_of, in_total);
 	build_runs(n, [&](size_t i, uintptr_t& p, size_t& len) {
-		p = reinterpret_cast<uintptr_t>(streams[i].dst);
-		len = streams[i].vertex_count * streams[i].vertex_size;
+		p = reinterpret_cast<uintptr_t>(host[i].dst);
+		len = host[i].vertex_count * host[i].vertex_size;
 	}, 0, out_runs, out_run_of, out_total);
 	if (ctx->d_in.reserve(in_total + 256) || ctx->d_out.reserve(out_total + 256))
 		return MOB200_ERR_CUDA;
 	uint8_t* d_in = static_cast<uint8_t*>(ctx->d_in.ptr);
 	uint8_t* d_out = static_cast<uint8_t*>(ctx->d_out.ptr);
 
-	std::vector<mob200_Stream> dev(streams, streams + n);
+	std::vector<mob200_Stream> dev(host);
 	for (size_t i = 0; i < n; ++i)
 	{
-		dev[i].src = streams[i].src ? d_in + run_device_offset(in_runs[in_run_of[i]], reinterpret_cast<uintptr_t>(streams[i].src)) : nullptr;
-		dev[i].dst = d_out + run_device_offset(out_runs[out_run_of[i]], reinterpret_cast<uintptr_t>(streams[i].dst));
+		dev[i].src = host[i].src ? d_in + run_device_offset(in_runs[in_run_of[i]], reinterpret_cast<uintptr_t>(host[i].src)) : nullptr;
+		dev[i].dst = d_out + run_device_offset(out_runs[out_run_of[i]], reinterpret_cast<uintptr_t>(host[i].dst));
 	}
 
 	// chunks of consecutive streams (~kChunkBytes of traffic each) rotate over kSlots in-flight slots
@@ -731,6 +755,7 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 	{
 		mob200_Plan* plan = nullptr;
 		size_t i0 = 0, i1 = 0;
+		bool recorded = false;
 		std::vector<std::pair<void*, std::pair<const void*, size_t>>> unstage; // dst <- (pinned staging, bytes)
 	};
 	SlotWork work[mob200_Context::kHostSlots];
@@ -739,16 +764,44 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 		SlotWork& w = work[k];
 		if (!w.plan)
 			return 0;
-		CUDA_TRY(cudaEventSynchronize(ctx->slot_done[k]));
-		for (auto& u : w.unstage)
-			memcpy(u.first, u.second.first, u.second.second);
+		int rc = 0;
+		if (w.recorded)
+		{
+			if (cudaEventSynchronize(ctx->slot_done[k]) != cudaSuccess)
+				rc = MOB200_ERR_CUDA;
+		}
+		else if (cudaStreamSynchronize(ctx->slot_stream[k]) != cudaSuccess) // (a chunk that failed half-way: whatever it enqueued must finish)
+			rc = MOB200_ERR_CUDA;
+		if (rc == 0 && w.recorded)
+		{
+			for (auto& u : w.unstage)
+				memcpy(u.first, u.second.first, u.second.second);
+			for (size_t i = w.i0; i < w.i1; ++i)
+				status[i] = h_status[i];
+		}
 		w.unstage.clear();
-		for (size_t i = w.i0; i < w.i1; ++i)
-			status[i] = h_status[i];
 		mob200_plan_destroy(w.plan);
 		w.plan = nullptr;
-		return 0;
+		w.recorded = false;
+		return rc;
 	};
+	// error path: nothing may stay in flight (DMA into caller memory, kernels, plans) when the call returns
+	auto fail = [&](int rc) -> int {
+		for (int k = 0; k < kSlots; ++k)
+			retire(k);
+		cudaGetLastError();
+		return rc;
+	};
+#define SLOT_TRY(expr)                                                                                                  \
+	do                                                                                                                  \
+	{                                                                                                                   \
+		cudaError_t err__ = (expr);                                                                                     \
+		if (err__ != cudaSuccess)                                                                                       \
+		{                                                                                                               \
+			fprintf(stderr, "meshopt_b200: %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+			return fail(MOB200_ERR_CUDA);                                                                               \
+		}                                                                                                               \
+	} while (0)
 
 	size_t chunk_index = 0;
 	for (size_t i0 = 0; i0 < n; ++chunk_index)
@@ -756,12 +809,12 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 		size_t i1 = i0, bytes = 0;
 		while (i1 < n && (i1 == i0 || bytes < kChunkBytes))
 		{
-			bytes += (streams[i1].src ? streams[i1].src_size : 0) + streams[i1].vertex_count * streams[i1].vertex_size;
+			bytes += (host[i1].src ? host[i1].src_size : 0) + host[i1].vertex_count * host[i1].vertex_size;
 			++i1;
 		}
 		const int k = (int)(chunk_index % kSlots);
 		if (retire(k))
-			return MOB200_ERR_CUDA;
+			return fail(MOB200_ERR_CUDA);
 		cudaStream_t st = ctx->slot_stream[k];
 		SlotWork& w = work[k];
 		w.i0 = i0;
@@ -775,7 +828,7 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 			size_t last = std::min(i1, r.first + r.count);
 			if (!r.pinned)
 				for (size_t j = i; j < last; ++j)
-					stage_need_in += align_up(streams[j].src ? streams[j].src_size : 0, 16) + 16;
+					stage_need_in += align_up(host[j].src ? host[j].src_size : 0, 16) + 16;
 			i = last;
 		}
 		for (size_t i = i0; i < i1;)
@@ -784,11 +837,11 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 			size_t last = std::min(i1, r.first + r.count);
 			if (!r.pinned)
 				for (size_t j = i; j < last; ++j)
-					stage_need_out += align_up(streams[j].vertex_count * streams[j].vertex_size, 16) + 16;
+					stage_need_out += align_up(host[j].vertex_count * host[j].vertex_size, 16) + 16;
 			i = last;
 		}
 		if ((stage_need_in && ctx->slot_h_in[k].reserve(stage_need_in)) || (stage_need_out && ctx->slot_h_out[k].reserve(stage_need_out)))
-			return MOB200_ERR_CUDA;
+			return fail(MOB200_ERR_CUDA);
 
 		size_t cursor = 0;
 		for (size_t i = i0; i < i1;)
@@ -796,9 +849,9 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 			const HostRun& r = in_runs[in_run_of[i]];
 			size_t last = std::min(i1, r.first + r.count);
 			// host range of streams [i, last) inside the run
-			uintptr_t h0 = reinterpret_cast<uintptr_t>(streams[i].src);
-			uintptr_t h1 = reinterpret_cast<uintptr_t>(streams[last - 1].src) + (streams[last - 1].src ? streams[last - 1].src_size : 0);
-			if (streams[i].src && h1 > h0)
+			uintptr_t h0 = reinterpret_cast<uintptr_t>(host[i].src);
+			uintptr_t h1 = reinterpret_cast<uintptr_t>(host[last - 1].src) + (host[last - 1].src ? host[last - 1].src_size : 0);
+			if (host[i].src && h1 > h0)
 			{
 				const void* from = reinterpret_cast<const void*>(h0);
 				if (!r.pinned)
@@ -808,18 +861,18 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 					from = hp;
 					cursor += align_up(h1 - h0, 16) + 16;
 				}
-				CUDA_TRY(cudaMemcpyAsync(d_in + run_device_offset(r, h0), from, h1 - h0, cudaMemcpyHostToDevice, st));
+				SLOT_TRY(cudaMemcpyAsync(d_in + run_device_offset(r, h0), from, h1 - h0, cudaMemcpyHostToDevice, st));
 			}
 			i = last;
 		}
 
-		// decode the chunk
-		int rc = plan_create_impl(ctx, dev.data() + i0, i1 - i0, &ctx->slot_arena[k], st, false, &w.plan);
+		// decode the chunk (block mode when every stream of it came with a block-offset sidecar)
+		int rc = plan_create_impl(ctx, dev.data() + i0, i1 - i0, &ctx->slot_arena[k], st, false, &w.plan, sidecars ? sidecars + i0 : nullptr);
 		if (rc)
-			return rc;
-		rc = mob200_plan_run(w.plan, st);
+			return fail(rc);
+		rc = mob200_plan_run_ex(w.plan, st, w.plan->have_offsets ? MOB200_RUN_BLOCK_PARALLEL : 0);
 		if (rc)
-			return rc;
+			return fail(rc);
 
 		// device -> host
 		cursor = 0;
@@ -827,8 +880,8 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 		{
 			const HostRun& r = out_runs[out_run_of[i]];
 			size_t last = std::min(i1, r.first + r.count);
-			uintptr_t h0 = reinterpret_cast<uintptr_t>(streams[i].dst);
-			uintptr_t h1 = reinterpret_cast<uintptr_t>(streams[last - 1].dst) + streams[last - 1].vertex_count * streams[last - 1].vertex_size;
+			uintptr_t h0 = reinterpret_cast<uintptr_t>(host[i].dst);
+			uintptr_t h1 = reinterpret_cast<uintptr_t>(host[last - 1].dst) + host[last - 1].vertex_count * host[last - 1].vertex_size;
 			if (h1 > h0 && r.bytes)
 			{
 				void* to = reinterpret_cast<void*>(h0);
@@ -839,23 +892,25 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 					to = hp;
 					cursor += align_up(h1 - h0, 16) + 16;
 				}
-				CUDA_TRY(cudaMemcpyAsync(to, d_out + run_device_offset(r, h0), h1 - h0, cudaMemcpyDeviceToHost, st));
+				SLOT_TRY(cudaMemcpyAsync(to, d_out + run_device_offset(r, h0), h1 - h0, cudaMemcpyDeviceToHost, st));
 			}
 			i = last;
 		}
-		CUDA_TRY(cudaMemcpyAsync(h_status + i0, w.plan->T.status, (i1 - i0) * sizeof(int), cudaMemcpyDeviceToHost, st));
-		CUDA_TRY(cudaEventRecord(ctx->slot_done[k], st));
+		SLOT_TRY(cudaMemcpyAsync(h_status + i0, w.plan->T.status, (i1 - i0) * sizeof(int), cudaMemcpyDeviceToHost, st));
+		SLOT_TRY(cudaEventRecord(ctx->slot_done[k], st));
+		w.recorded = true;
 		i0 = i1;
 	}
 	for (int k = 0; k < kSlots; ++k)
 		if (retire(k))
-			return MOB200_ERR_CUDA;
+			return fail(MOB200_ERR_CUDA);
+#undef SLOT_TRY
 
 	int failed = 0;
 	for (size_t i = 0; i < n; ++i)
 	{
-		streams[i].status = status[i];
-		failed += status[i] != 0;
+		streams[i].status = skipped[i] ? MOB200_ERR_ARGUMENT : status[i];
+		failed += streams[i].status != 0;
 	}
 	return failed;
 }
@@ -864,25 +919,65 @@ extern "C" int mob200_decode_batch_host(mob200_Context* ctx, mob200_Stream* stre
 // drop-in symbols
 // ------------------------------------------------------------------------------------------------
 
-static mob200_Context* default_context();
-
-// (shared with mob200_index.cu; not exported: the library is built with hidden visibility)
-extern "C" mob200_Context* mob200_default_context(void)
+// pool of contexts for the drop-in symbols: at most kPoolMax per device, created on demand; a caller that finds
+// none free waits for one
+namespace
 {
-	return default_context();
+struct ContextPool
+{
+	std::mutex mu;
+	std::condition_variable cv;
+	std::vector<mob200_Context*> idle;
+	int created = 0;
+};
+const int kPoolMax = 8;
+ContextPool g_pools[64];
+} // namespace
+
+mob200_Context* mob200_pool_acquire()
+{
+	int device = 0;
+	if (cudaGetDevice(&device) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	ContextPool& pool = g_pools[device & 63];
+	std::unique_lock<std::mutex> lock(pool.mu);
+	for (;;)
+	{
+		if (!pool.idle.empty())
+		{
+			mob200_Context* ctx = pool.idle.back();
+			pool.idle.pop_back();
+			return ctx;
+		}
+		if (pool.created < kPoolMax)
+		{
+			++pool.created;
+			lock.unlock();
+			mob200_Context* ctx = nullptr;
+			if (mob200_context_create(&ctx, device) != 0)
+			{
+				lock.lock();
+				--pool.created;
+				pool.cv.notify_one();
+				return nullptr;
+			}
+			return ctx;
+		}
+		pool.cv.wait(lock);
+	}
 }
 
-static mob200_Context* default_context()
+void mob200_pool_release(mob200_Context* ctx)
 {
-	static std::mutex mu;
-	static mob200_Context* ctx = nullptr;
-	std::lock_guard<std::mutex> lock(mu);
-	if (!ctx)
+	ContextPool& pool = g_pools[ctx->device & 63];
 	{
-		if (mob200_context_create(&ctx, -1) != 0)
-			ctx = nullptr;
+		std::lock_guard<std::mutex> lock(pool.mu);
+		pool.idle.push_back(ctx);
 	}
-	return ctx;
+	pool.cv.notify_one();
 }
 
 extern "C" int meshopt_decodeVertexVersion(const unsigned char* buffer, size_t buffer_size)
@@ -899,7 +994,8 @@ extern "C" int meshopt_decodeVertexVersion(const unsigned char* buffer, size_t b
 
 extern "C" int meshopt_decodeVertexBuffer(void* destination, size_t vertex_count, size_t vertex_size, const unsigned char* buffer, size_t buffer_size)
 {
-	mob200_Context* ctx = default_context();
+	PoolLease lease;
+	mob200_Context* ctx = lease.ctx;
 	if (!ctx)
 		return MOB200_ERR_CUDA;
 	mob200_Stream s;
@@ -923,7 +1019,8 @@ static void filter_host(int filter, void* buffer, size_t count, size_t stride)
 	}
 	if (count == 0)
 		return;
-	mob200_Context* ctx = default_context();
+	PoolLease lease;
+	mob200_Context* ctx = lease.ctx;
 	if (!ctx)
 	{
 		fprintf(stderr, "meshopt_b200: no CUDA device available for meshopt_decodeFilter*\n");

@@ -35,8 +35,21 @@ struct Json
 	const char* p;
 	const char* end;
 	bool ok;
+	int depth; // nesting of the value being read: an untrusted asset must not be able to exhaust the host stack
+	static const int kMaxDepth = 64;
 
-	Json(const char* b, const char* e) : p(b), end(e), ok(true) {}
+	Json(const char* b, const char* e) : p(b), end(e), ok(true), depth(0) {}
+
+	bool enter()
+	{
+		if (++depth > kMaxDepth)
+		{
+			fail();
+			return false;
+		}
+		return true;
+	}
+	void leave() { --depth; }
 
 	void ws()
 	{
@@ -176,6 +189,8 @@ struct Json
 			++p;
 			if (eat('}'))
 				return;
+			if (!enter())
+				return;
 			do
 			{
 				std::string k;
@@ -186,6 +201,7 @@ struct Json
 				}
 				skip();
 			} while (ok && eat(','));
+			leave();
 			if (!eat('}'))
 				fail();
 		}
@@ -194,9 +210,12 @@ struct Json
 			++p;
 			if (eat(']'))
 				return;
+			if (!enter())
+				return;
 			do
 				skip();
 			while (ok && eat(','));
+			leave();
 			if (!eat(']'))
 				fail();
 		}
@@ -225,6 +244,8 @@ void each_member(Json& j, F f)
 	}
 	if (j.eat('}'))
 		return;
+	if (!j.enter())
+		return;
 	do
 	{
 		std::string key;
@@ -235,6 +256,7 @@ void each_member(Json& j, F f)
 		}
 		f(key);
 	} while (j.ok && j.eat(','));
+	j.leave();
 	if (!j.eat('}'))
 		j.fail();
 }
@@ -249,10 +271,13 @@ void each_element(Json& j, F f)
 	}
 	if (j.eat(']'))
 		return;
+	if (!j.enter())
+		return;
 	size_t index = 0;
 	do
 		f(index++);
 	while (j.ok && j.eat(','));
+	j.leave();
 	if (!j.eat(']'))
 		j.fail();
 }
@@ -315,6 +340,9 @@ void parse_extension(Json& j, ViewFields& v)
 bool view_valid(const ViewFields& v)
 {
 	if (v.bad || !v.have_mode || v.mode < 0)
+		return false;
+	// (sizes come from untrusted JSON: no product may wrap, and the codecs address 32-bit counts and sizes)
+	if (v.count >= 0xffffffffull || v.src_size >= 0xffffffffull || v.stride > 256)
 		return false;
 	if (v.length != v.count * v.stride)
 		return false;
@@ -453,6 +481,27 @@ extern "C" int mob200_gltf_scan(const void* data, size_t size, mob200_GltfView* 
 	if (!j.ok)
 		return MOB200_ERR_ARGUMENT;
 
+	// a view that names a buffer the asset does not have, or a range outside its buffers, is invalid (cgltf_validate
+	// rejects the asset, extern/cgltf.h:1645-1667); buffers[] may follow bufferViews[] in the text, hence this pass
+	if (views)
+		for (size_t k = 0; k < n_views && k < view_capacity; ++k)
+		{
+			mob200_GltfView& o = views[k];
+			if (o.status != 0)
+				continue;
+			bool bad = o.src_buffer >= n_buffers || o.dst_buffer >= n_buffers;
+			if (!bad && buffer_sizes && o.src_buffer < buffer_capacity && o.dst_buffer < buffer_capacity)
+			{
+				const size_t sb = buffer_sizes[o.src_buffer], db = buffer_sizes[o.dst_buffer];
+				bad = o.src_offset > sb || o.src_size > sb - o.src_offset || o.dst_offset > db || o.dst_size > db - o.dst_offset;
+			}
+			if (bad)
+			{
+				o.status = MOB200_ERR_ARGUMENT;
+				++n_invalid;
+			}
+		}
+
 	info->buffer_count = n_buffers;
 	info->view_count = n_views;
 	info->invalid_views = n_invalid;
@@ -463,9 +512,10 @@ namespace
 {
 
 // shared by the host and device entry points: views -> stream descriptors of the two codec families
-int decode_views(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs, bool device, void* cuda_stream)
+int decode_views(mob200_Context* ctx, mob200_GltfView* views, size_t n, size_t buffer_count, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs, const size_t* output_sizes,
+    bool device, void* cuda_stream)
 {
-	if (!ctx || (!views && n))
+	if (!ctx || (!views && n) || (n && (!buffers || !buffer_sizes || !outputs || !output_sizes)))
 		return MOB200_ERR_ARGUMENT;
 
 	std::vector<mob200_Stream> vstreams;
@@ -477,9 +527,14 @@ int decode_views(mob200_Context* ctx, mob200_GltfView* views, size_t n, const vo
 		if (v.status == MOB200_ERR_ARGUMENT) // rejected by the scan
 			continue;
 		v.status = MOB200_ERR_ARGUMENT;
-		if (!buffers || !outputs || !buffers[v.src_buffer] || !outputs[v.dst_buffer])
+		// every index and range of a view comes from the asset's JSON: nothing is dereferenced before it is bounded
+		if (v.src_buffer >= buffer_count || v.dst_buffer >= buffer_count || !buffers[v.src_buffer] || !outputs[v.dst_buffer])
 			continue;
-		if (buffer_sizes && (v.src_offset > buffer_sizes[v.src_buffer] || v.src_size > buffer_sizes[v.src_buffer] - v.src_offset))
+		if (v.src_offset > buffer_sizes[v.src_buffer] || v.src_size > buffer_sizes[v.src_buffer] - v.src_offset)
+			continue;
+		if (v.count >= 0xffffffffull || v.stride == 0 || v.stride > 256 || v.dst_size != v.count * v.stride)
+			continue;
+		if (v.dst_offset > output_sizes[v.dst_buffer] || v.dst_size > output_sizes[v.dst_buffer] - v.dst_offset)
 			continue;
 		const unsigned char* src = static_cast<const unsigned char*>(buffers[v.src_buffer]) + v.src_offset;
 		unsigned char* dst = static_cast<unsigned char*>(outputs[v.dst_buffer]) + v.dst_offset;
@@ -534,12 +589,12 @@ int decode_views(mob200_Context* ctx, mob200_GltfView* views, size_t n, const vo
 
 } // namespace
 
-extern "C" int mob200_gltf_decode_host(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs)
+extern "C" int mob200_gltf_decode_host(mob200_Context* ctx, mob200_GltfView* views, size_t n, size_t buffer_count, const void* const* buffers, const size_t* buffer_sizes, void* const* outputs, const size_t* output_sizes)
 {
-	return decode_views(ctx, views, n, buffers, buffer_sizes, outputs, false, nullptr);
+	return decode_views(ctx, views, n, buffer_count, buffers, buffer_sizes, outputs, output_sizes, false, nullptr);
 }
 
-extern "C" int mob200_gltf_decode_device(mob200_Context* ctx, mob200_GltfView* views, size_t n, const void* const* device_buffers, const size_t* buffer_sizes, void* const* device_outputs, void* cuda_stream)
+extern "C" int mob200_gltf_decode_device(mob200_Context* ctx, mob200_GltfView* views, size_t n, size_t buffer_count, const void* const* device_buffers, const size_t* buffer_sizes, void* const* device_outputs, const size_t* output_sizes, void* cuda_stream)
 {
-	return decode_views(ctx, views, n, device_buffers, buffer_sizes, device_outputs, true, cuda_stream);
+	return decode_views(ctx, views, n, buffer_count, device_buffers, buffer_sizes, device_outputs, output_sizes, true, cuda_stream);
 }

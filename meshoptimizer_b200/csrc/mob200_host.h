@@ -101,3 +101,23 @@ static inline int set_device(const mob200_Context* ctx)
 	CUDA_TRY(cudaSetDevice(ctx->device));
 	return 0;
 }
+
+// Contexts of the drop-in symbols (host pointers, synchronous, callable from many threads at once -- reference
+// contract src/meshoptimizer.h, SURVEY.md section 8b "Threading"): a small pool per device, one context per call in
+// flight, so that concurrent callers overlap their copies (kernels are chained per device, mob200_api.cu).
+// Hidden visibility: shared by the translation units of the library only.
+mob200_Context* mob200_pool_acquire();
+void mob200_pool_release(mob200_Context* ctx);
+
+struct PoolLease
+{
+	mob200_Context* ctx;
+	PoolLease() : ctx(mob200_pool_acquire()) {}
+	~PoolLease()
+	{
+		if (ctx)
+			mob200_pool_release(ctx);
+	}
+	PoolLease(const PoolLease&) = delete;
+	PoolLease& operator=(const PoolLease&) = delete;
+};

@@ -411,11 +411,11 @@ extern "C" int mob200_decode_index_batch_host(mob200_Context* ctx, mob200_IndexS
 // drop-in symbols (reference src/meshoptimizer.h:344,351,376): host pointers, synchronous
 // ------------------------------------------------------------------------------------------------
 
-extern "C" mob200_Context* mob200_default_context(void); // mob200_api.cu: the lazily created context of the drop-in symbols
 
 static int decode_index_dropin(int kind, void* destination, size_t index_count, size_t index_size, const unsigned char* buffer, size_t buffer_size)
 {
-	mob200_Context* ctx = mob200_default_context();
+	PoolLease lease;
+	mob200_Context* ctx = lease.ctx;
 	if (!ctx)
 		return MOB200_ERR_CUDA;
 	mob200_IndexStream s;

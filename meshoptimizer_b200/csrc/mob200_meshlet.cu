@@ -273,11 +273,11 @@ extern "C" int mob200_decode_meshlet_batch_host(mob200_Context* ctx, mob200_Mesh
 // drop-in symbols (reference src/meshoptimizer.h:349-350): host pointers, synchronous
 // ------------------------------------------------------------------------------------------------
 
-extern "C" mob200_Context* mob200_default_context(void);
 
 extern "C" int meshopt_decodeMeshlet(void* vertices, size_t vertex_count, size_t vertex_size, void* triangles, size_t triangle_count, size_t triangle_size, const unsigned char* buffer, size_t buffer_size)
 {
-	mob200_Context* ctx = mob200_default_context();
+	PoolLease lease;
+	mob200_Context* ctx = lease.ctx;
 	if (!ctx)
 		return MOB200_ERR_CUDA;
 	mob200_Meshlet m;

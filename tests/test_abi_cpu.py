@@ -71,3 +71,30 @@ def test_product_never_imports_oracle():
 def test_stream_struct_layout():
     import meshoptimizer_b200 as mb
     assert ctypes.sizeof(mb.Stream) == 48
+
+
+def test_gltf_scan_rejects_hostile_json():
+    """unbounded recursion and unchecked buffer indices / ranges in the glTF scanner"""
+    import json
+
+    import meshoptimizer_b200 as mb
+
+    deep = ("[" * 200000).encode()
+    with pytest.raises(ValueError):
+        mb.gltf_scan(np.frombuffer(b'{"extras":' + deep + b"}", dtype=np.uint8))
+    ext = {"buffer": 0, "byteOffset": 0, "byteLength": 40, "byteStride": 4, "count": 10, "mode": "ATTRIBUTES"}
+    doc = {
+        "buffers": [{"byteLength": 64}, {"byteLength": 40}],
+        "bufferViews": [
+            {"buffer": 1, "byteOffset": 0, "byteLength": 40, "extensions": {"EXT_meshopt_compression": dict(ext)}},
+            {"buffer": 9, "byteOffset": 0, "byteLength": 40, "extensions": {"EXT_meshopt_compression": dict(ext)}},            # no such buffer
+            {"buffer": 1, "byteOffset": 8, "byteLength": 40, "extensions": {"EXT_meshopt_compression": dict(ext)}},            # destination beyond buffers[1]
+            {"buffer": 1, "byteOffset": 0, "byteLength": 40, "extensions": {"EXT_meshopt_compression": dict(ext, byteOffset=30)}},  # source beyond buffers[0]
+            {"buffer": 1, "byteOffset": 0, "byteLength": 2 ** 42, "extensions": {"EXT_meshopt_compression": dict(ext, count=2 ** 40, byteStride=4)}},  # count >= 2^32
+            {"buffer": 1, "byteOffset": 0, "byteLength": 40, "extensions": {"EXT_meshopt_compression": dict(ext, buffer=5)}},   # no such source buffer
+        ],
+    }
+    views, sizes, info = mb.gltf_scan(np.frombuffer(json.dumps(doc).encode(), dtype=np.uint8))
+    assert info.view_count == 6 and sizes == [64, 40]
+    assert [views[i].status for i in range(6)] == [0, mb.ERR_ARGUMENT, mb.ERR_ARGUMENT, mb.ERR_ARGUMENT, mb.ERR_ARGUMENT, mb.ERR_ARGUMENT]
+    assert info.invalid_views == 5

@@ -150,14 +150,25 @@ def test_gltf_device_variant_and_bad_view(mb):
     bufs = (ctypes.c_void_p * 2)(d_bin.data_ptr(), None)
     outs = (ctypes.c_void_p * 2)(None, d_out.data_ptr())
     lens = (ctypes.c_size_t * 2)(info.bin_size, 0)
-    rc = mb.lib().mob200_gltf_decode_device(mb.default_context().handle, views, info.view_count, bufs, lens, outs, None)
+    olens = (ctypes.c_size_t * 2)(0, sizes[1])
+    rc = mb.lib().mob200_gltf_decode_device(mb.default_context().handle, views, info.view_count, 2, bufs, lens, outs, olens, None)
     assert rc == 0
     assert np.array_equal(d_out.cpu().numpy()[: sizes[1]], expected)
     # a view whose compressed range is cut short fails with the codec's own code; the others still decode
     views2, _, _ = mb.gltf_scan(blob)
     views2[0].src_size -= 5
-    rc = mb.lib().mob200_gltf_decode_device(mb.default_context().handle, views2, info.view_count, bufs, lens, outs, None)
+    rc = mb.lib().mob200_gltf_decode_device(mb.default_context().handle, views2, info.view_count, 2, bufs, lens, outs, olens, None)
     assert rc == 1 and views2[0].status in (-2, -3) and all(views2[i].status == 0 for i in range(1, info.view_count))
+    # views are untrusted: a buffer index beyond the asset's buffers, a destination range beyond its buffer and a
+    # source range beyond its buffer are rejected before anything is read or written (guard bytes stay)
+    views3, _, _ = mb.gltf_scan(blob)
+    views3[0].dst_buffer = 7
+    views3[1].dst_offset = sizes[1] - 4
+    views3[2].src_offset = info.bin_size - 3
+    d_out.fill_(0xCD)
+    rc = mb.lib().mob200_gltf_decode_device(mb.default_context().handle, views3, info.view_count, 2, bufs, lens, outs, olens, None)
+    assert rc == 3 and all(views3[i].status == mb.ERR_ARGUMENT for i in range(3)) and all(views3[i].status == 0 for i in range(3, info.view_count))
+    assert (d_out.cpu().numpy()[sizes[1]:] == 0xCD).all()
 
 
 # ---- meshlets ---------------------------------------------------------------------------------------
