@@ -20,6 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "_build", "libmeshopt_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libmeshopt_ref.so")
+REF_AVX_SO = os.path.join(HERE, "_ref", "libmeshopt_ref_avx.so")  # same sources, -mavx: CPU-baseline timing only
 
 FILTER_NONE, FILTER_OCT, FILTER_QUAT, FILTER_EXP, FILTER_COLOR = 0, 1, 2, 3, 4
 FILTER_NAMES = {"none": 0, "oct": 1, "quat": 2, "exp": 3, "color": 4}
@@ -52,6 +53,8 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-s", "-C", HERE, "port"])
     if os.path.isdir("/root/reference/src") and (force or not os.path.exists(REF_SO) or _stale(REF_SO)):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    if os.path.isdir("/root/reference/src") and (force or not os.path.exists(REF_AVX_SO) or _stale(REF_AVX_SO)):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref_avx"])
 
 
 def _stale(so: str) -> bool:
@@ -170,7 +173,8 @@ class _Lib:
         for i, (src, count, vs, filt) in enumerate(streams):
             s = _u8(src)
             keep.append(s)
-            o = np.zeros(max(count * vs, 1), dtype=np.uint8)
+            o = np.empty(max(count * vs, 1), dtype=np.uint8)
+            o.fill(0)  # pre-faulted: the timed passes never pay for first-touch page faults
             outs.append(o)
             arr[i].src = s.ctypes.data
             arr[i].src_size = s.size
@@ -217,8 +221,8 @@ class _Lib:
 class _Ref(_Lib):
     """The unmodified reference: adds the encoders (input generation)."""
 
-    def __init__(self):
-        super().__init__(REF_SO, "meshopt_", "reference")
+    def __init__(self, path: str = REF_SO, kind: str = "reference"):
+        super().__init__(path, "meshopt_", kind)
         L = self.lib
         L.meshopt_encodeVertexBufferLevel.restype = c_size_t
         L.meshopt_encodeVertexBufferLevel.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_int]
@@ -333,6 +337,21 @@ def port() -> _Lib:
 
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
+
+
+_ref_avx = None
+
+
+def have_ref_avx() -> bool:
+    return os.path.exists(REF_AVX_SO)
+
+
+def ref_avx() -> _Ref:
+    """the reference compiled with -mavx (timing only; parity always uses ref())"""
+    global _ref_avx
+    if _ref_avx is None:
+        _ref_avx = _Ref(REF_AVX_SO, "reference")
+    return _ref_avx
 
 
 def ref() -> _Ref:
