@@ -192,7 +192,7 @@ __device__ __forceinline__ unsigned long long* debug_counters(const DevTables& T
 	return reinterpret_cast<unsigned long long*>(T.counters + 16);
 }
 
-template <bool kRounds>
+template <bool kRounds, bool kBlock>
 __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t unit)
 {
 	using L = Lay<kRounds>;
@@ -334,7 +334,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		for (uint32_t j0 = 0; kRounds ? j0 < in_batch : jc < in_batch;)
 		{
 			bool plain_stage = !kRounds && js < in_batch && js == jc;
-			if (!kRounds && js < in_batch && js == jc + 1)
+			if (!kRounds && kBlock && js < in_batch && js == jc + 1)
 			{
 				// one block ahead of the carry -- but only if its ring piece can be had without waiting for block jc itself
 				// (whose decoders wait for the carry this warp has not resolved yet): with jc the only live piece the
@@ -486,7 +486,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 							S.P.round_members = round_members;
 						mbar_arrive(full + slot);
 					}
-					if (T.block_mode)
+					if (kBlock)
 					{
 						// block mode: later blocks of the stream may still be decodable (their output is garbage, as the
 						// reference allows for a rejected stream) and must not wait for this block's look-back entries
@@ -525,7 +525,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 							S.carry[q0 + 3] = (uint32_t)pre3;
 					}
 				}
-				if (valid && !carry_done && b > 0 && nq <= 32)
+				if (kBlock && valid && !carry_done && b > 0 && nq <= 32)
 				{
 					// Decoupled look-back, 32 / nqp predecessors per step (nqp = nq rounded up to a power of two): lane =
 					// (predecessor pj, 4-byte lane q).  Per q the lanes consume the leading run of published predecessors up

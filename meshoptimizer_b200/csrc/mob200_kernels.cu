@@ -38,7 +38,9 @@ static_assert(kSmemWalkerBytes >= kWalkSmemBytes && kSmemWalkerBytes >= kWideSme
 // kWideWalk: one walker warp per stream (few streams) instead of one lane per stream.
 // kRounds:   blocks of small vertices (<= 16 bytes: one or two work quanta) are decoded up to four at a time by a unit's
 //            four decoder warps (Lay<true>); otherwise one block at a time goes round the four warps.
-template <bool kWideWalk, bool kRounds>
+// kBlock:    block mode (DevTables::block_mode): one walker lane per BLOCK from the block-offset table, look-back over
+//            several predecessors per step.  A template parameter so that a kernel carries the code of one mode only.
+template <bool kWideWalk, bool kRounds, bool kBlock>
 __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 {
 	using L = Lay<kRounds>;
@@ -95,16 +97,16 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 	else if (role == 1)
 	{
 		if (decode_on)
-			producer_main<kRounds>(T, smem, unit);
+			producer_main<kRounds, kBlock>(T, smem, unit);
 	}
-	else if (walk_on && (g < 4 || (T.block_mode ? T.total_blocks : T.n_streams) > 4u * (kWideWalk ? 1u : 32u) * gridDim.x))
+	else if (walk_on && (g < 4 || (kBlock ? T.total_blocks : T.n_streams) > 4u * (kWideWalk ? 1u : 32u) * gridDim.x))
 	{
 		// (the fifth walker shares a scheduler with the first: it only runs when four per SM cannot take every
 		// stream in one round -- one walker per scheduler is 9% faster alone and 3% faster fused)
 		if (kWideWalk)
 			walker_main_wide(T, smem + L::kSmemWalker);
 		else
-			walker_main(T, smem + L::kSmemWalker);
+			walker_main<kBlock>(T, smem + L::kSmemWalker);
 	}
 
 #ifdef MOB200_DEBUG_ENDS
@@ -204,25 +206,41 @@ __global__ void __launch_bounds__(256) filter_kernel(uint8_t* data, size_t count
 // launchers
 // ------------------------------------------------------------------------------------------------
 
+template <bool kWideWalk, bool kRounds, bool kBlock>
+static cudaError_t prepare_one()
+{
+	return cudaFuncSetAttribute(decode_kernel<kWideWalk, kRounds, kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<kRounds>::kSmemCta);
+}
+
 cudaError_t prepare_decode_kernel()
 {
-	cudaError_t err = cudaFuncSetAttribute(decode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<false>::kSmemCta);
+	cudaError_t err = prepare_one<false, false, false>();
 	if (err == cudaSuccess)
-		err = cudaFuncSetAttribute(decode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<false>::kSmemCta);
+		err = prepare_one<true, false, false>();
 	if (err == cudaSuccess)
-		err = cudaFuncSetAttribute(decode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<true>::kSmemCta);
+		err = prepare_one<false, true, false>();
 	if (err == cudaSuccess)
-		err = cudaFuncSetAttribute(decode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<true>::kSmemCta);
+		err = prepare_one<true, true, false>();
+	if (err == cudaSuccess)
+		err = prepare_one<false, false, true>();
+	if (err == cudaSuccess)
+		err = prepare_one<false, true, true>();
 	return err;
 }
 
 cudaError_t decode_occupancy(int* ctas_per_sm)
 {
-	int a = 0, b = 0;
-	cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, decode_kernel<false, false>, kCtaThreads, Lay<false>::kSmemCta);
+	int a = 0, b = 0, c = 0, d = 0;
+	cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, decode_kernel<false, false, false>, kCtaThreads, Lay<false>::kSmemCta);
 	if (err == cudaSuccess)
-		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, decode_kernel<false, true>, kCtaThreads, Lay<true>::kSmemCta);
-	*ctas_per_sm = a < b ? a : b;
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, decode_kernel<false, true, false>, kCtaThreads, Lay<true>::kSmemCta);
+	if (err == cudaSuccess)
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, decode_kernel<false, false, true>, kCtaThreads, Lay<false>::kSmemCta);
+	if (err == cudaSuccess)
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, decode_kernel<false, true, true>, kCtaThreads, Lay<true>::kSmemCta);
+	int m = a < b ? a : b;
+	m = m < c ? m : c;
+	*ctas_per_sm = m < d ? m : d;
 	return err;
 }
 
@@ -230,19 +248,27 @@ cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream
 {
 	if (T.n_streams == 0)
 		return cudaSuccess;
-	if (T.rounds)
+	if (T.block_mode)
+	{
+		// (one walker lane per block: the wide form has no part in it)
+		if (T.rounds)
+			decode_kernel<false, true, true><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
+		else
+			decode_kernel<false, false, true><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
+	}
+	else if (T.rounds)
 	{
 		if (T.wide_walk)
-			decode_kernel<true, true><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
+			decode_kernel<true, true, false><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
 		else
-			decode_kernel<false, true><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
+			decode_kernel<false, true, false><<<grid, kCtaThreads, Lay<true>::kSmemCta, stream>>>(T);
 	}
 	else
 	{
 		if (T.wide_walk)
-			decode_kernel<true, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
+			decode_kernel<true, false, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
 		else
-			decode_kernel<false, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
+			decode_kernel<false, false, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
 	}
 	return cudaGetLastError();
 }

@@ -408,9 +408,10 @@ __device__ __forceinline__ int walk_framing(const uint8_t* src, uint32_t size, u
 //     walk ends exactly where the table says the next block starts (the padded tail for the last block) and block 0
 //     starts at byte 1: the union of all verified blocks is then the chain the serial walk would have followed.
 //     Anything else marks the stream kStatusSidecar.
+template <bool kBlock>
 __device__ void walk_group(const DevTables& T, WalkWarp& W, uint32_t base, uint32_t lane, uint32_t ring_smem)
 {
-	const bool bm = T.block_mode != 0;
+	constexpr bool bm = kBlock; // (a template parameter: each kernel carries the code of one mode only -- the roles share the SM's instruction cache)
 	const uint32_t job = base + lane;
 	const bool have = job < (bm ? T.total_blocks : T.n_streams);
 	uint32_t s = have ? job : 0, b_first = 0;
@@ -526,6 +527,7 @@ __device__ void walk_frame_group(const DevTables& T, uint32_t base, uint32_t lan
 		T.status[d->caller_index] = status;
 }
 
+template <bool kBlock>
 __device__ void walker_main(const DevTables& T, uint8_t* region)
 {
 	const uint32_t lane = threadIdx.x & 31u;
@@ -551,7 +553,7 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 		if (lane == 0)
 			base = atomicAdd(T.counters + 1, 32u);
 		base = __shfl_sync(0xffffffffu, base, 0);
-		if (T.block_mode && base >= ticket_span)
+		if (kBlock && base >= ticket_span)
 		{
 			if (T.n_with_blocks + (base - ticket_span) >= T.n_streams)
 				break;
@@ -559,9 +561,9 @@ __device__ void walker_main(const DevTables& T, uint8_t* region)
 		}
 		else
 		{
-			if (!T.block_mode && base >= T.n_streams)
+			if (!kBlock && base >= T.n_streams)
 				break;
-			walk_group(T, W, base, lane, ring_smem);
+			walk_group<kBlock>(T, W, base, lane, ring_smem);
 		}
 		__syncwarp();
 	}
