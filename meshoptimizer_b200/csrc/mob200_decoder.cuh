@@ -32,7 +32,8 @@ constexpr uint32_t kRoundBlocks = 4;           // rounds variant: blocks the dec
 constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight
 constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
-constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
+constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile (conflict-free column writes)
+constexpr uint32_t kTilePadTma = 16;           // ... of a tile that leaves by TMA bulk stores (the chunks must start on 16-byte boundaries; 2-way conflicts)
 
 struct BlockParams // written by the producer, read by the decoders after the slot's `full` barrier (80 bytes)
 {
@@ -52,7 +53,7 @@ struct BlockParams // written by the producer, read by the decoders after the sl
 	const uint16_t* rows_global;
 	unsigned long long* lookback; // this block's entries (vs/4 of them); predecessors lie vs/4 entries lower each
 	uint32_t round_members;       // rounds variant: > 0: this block opens a decode round of so many consecutive blocks; 0: it continues one
-	uint32_t pad;
+	uint32_t tma_out;             // plain form: the tile leaves by TMA bulk stores (no filter, 16-byte aligned destination and size)
 };
 
 struct SlotData
@@ -71,13 +72,13 @@ template <bool kRounds>
 struct Lay
 {
 	static constexpr uint32_t kSlots = kRounds ? 8 : 4; // blocks in flight between producer and decoders
-	static constexpr uint32_t kTileBytes = kBlockBytes + (kRounds ? kRoundBlocks : 1) * 16 * kTilePad; // one 8 KB block, or up to four smaller ones side by side
+	static constexpr uint32_t kTileBytes = kBlockBytes + (kRounds ? kRoundBlocks * 16 * kTilePad : 16 * kTilePadTma); // one 8 KB block, or up to four smaller ones side by side
 	static constexpr uint32_t kSmemStage = 0;
 	static constexpr uint32_t kSmemTile = kSmemStage + kStageRingBytes;
 	static constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;            // escape-byte selector table: 16 x 4 bytes
 	static constexpr uint32_t kSmemSlots = kSmemPatch + 64;
-	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
-	static constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;   // producer-private: ring_start[kSlots], ring_len[kSlots]
+	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free, tile_done
+	static constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 2) * 8;   // producer-private: ring_start[kSlots], ring_len[kSlots]
 	static constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
 	static constexpr uint32_t kSmemTotal = (kSmemWalker + 32 * 512 + 6 * 4 * 32 + 16 + 1023) & ~1023u; // one unit
 	static constexpr uint32_t kSmemCta = kSmemTotal * kUnitsPerCta;
@@ -114,9 +115,9 @@ __device__ __forceinline__ uint32_t lane_mask(uint32_t channel)
 
 // output tile: row r (vertex) of vs bytes; every 16-row chunk is displaced by kTilePad bytes so that the
 // 4-byte column writes of the 16 chunks of a lane (16 threads of one warp) fall into different banks
-__device__ __forceinline__ uint32_t tile_offset(uint32_t r, uint32_t vs)
+__device__ __forceinline__ uint32_t tile_offset(uint32_t r, uint32_t vs, uint32_t pad = kTilePad)
 {
-	return r * vs + (r >> 4) * kTilePad;
+	return r * vs + (r >> 4) * pad;
 }
 
 #ifdef MOB200_DEBUG_ENDS
@@ -465,6 +466,11 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						P.lookback = reinterpret_cast<unsigned long long*>(m_look);
 						if (kRounds)
 							P.round_members = round_members;
+#ifndef MOB200_NO_TMA_STORE
+						P.tma_out = (!kRounds && m_filter == MOB200_FILTER_NONE && ((m_out | (unsigned long long)(m_n * vs)) & 15ull) == 0) ? 1u : 0u;
+#else
+						P.tma_out = 0;
+#endif
 
 						fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
 						mbar_expect_tx(full + slot, len);
@@ -675,6 +681,20 @@ __device__ __forceinline__ uint32_t patch_selector(uint32_t idx)
 	return sel;
 }
 
+#ifdef MOB200_SHARED_PATCH
+// (variant: ONE copy of the escape-byte merge for the four unpack copies of a work item)
+__device__ __noinline__ uint4 patch_group(const uint8_t* ring, uint4 r, uint32_t esc, uint32_t idx, const uint32_t* patch_lut)
+{
+	const uint32_t i0 = idx & 15u, i1 = (idx >> 4) & 15u, i2 = (idx >> 8) & 15u, i3 = idx >> 12;
+	const uint32_t e1 = esc + __popc(i0), e2 = e1 + __popc(i1), e3 = e2 + __popc(i2);
+	r.x = __byte_perm(r.x, lds_u32_at(ring, esc), patch_lut[i0]);
+	r.y = __byte_perm(r.y, lds_u32_at(ring, e1), patch_lut[i1]);
+	r.z = __byte_perm(r.z, lds_u32_at(ring, e2), patch_lut[i2]);
+	r.w = __byte_perm(r.w, lds_u32_at(ring, e3), patch_lut[i3]);
+	return r;
+}
+#endif
+
 // (inlined: the four groups of a work item interleave; as a call the fused kernel is 4% slower, the decoders alone 9%)
 __device__ __forceinline__ uint4 unpack_group(
     const uint8_t* ring, uint32_t base, uint32_t entry, const uint32_t* patch_lut)
@@ -737,6 +757,9 @@ __device__ __forceinline__ uint4 unpack_group(
 	const uint32_t i0 = sentinel_index(r.x, bias), i1 = sentinel_index(r.y, bias), i2 = sentinel_index(r.z, bias), i3 = sentinel_index(r.w, bias);
 	if ((i0 | i1 | i2 | i3) == 0)
 		return r;
+#ifdef MOB200_SHARED_PATCH
+	return patch_group(ring, r, esc, i0 | (i1 << 4) | (i2 << 8) | (i3 << 12), patch_lut);
+#else
 	// (the 32-bit windows may reach a few bytes past the last escape byte: still inside the staging ring, never selected)
 	const uint32_t e1 = esc + __popc(i0), e2 = e1 + __popc(i1), e3 = e2 + __popc(i2);
 	r.x = __byte_perm(r.x, lds_u32_at(ring, esc), patch_lut[i0]);
@@ -744,11 +767,12 @@ __device__ __forceinline__ uint4 unpack_group(
 	r.z = __byte_perm(r.z, lds_u32_at(ring, e2), patch_lut[i2]);
 	r.w = __byte_perm(r.w, lds_u32_at(ring, e3), patch_lut[i3]);
 	return r;
+#endif
 }
 
 struct BlockRegs
 {
-	uint32_t vs, n, groups, gshift, items, stage_off, rows_off, filter, filter_kind, m_chunk;
+	uint32_t vs, n, groups, gshift, items, stage_off, rows_off, filter, filter_kind, m_chunk, tile_pad;
 	bool first_block;
 	const uint16_t* rows_global;
 	uint8_t* out;
@@ -767,6 +791,7 @@ __device__ __forceinline__ BlockRegs load_block(const SlotData& S)
 	B.rows_global = S.P.rows_global;
 	B.out = S.P.out;
 	B.lookback = S.P.lookback;
+	B.tile_pad = S.P.tma_out ? kTilePadTma : kTilePad;
 	return B;
 }
 
@@ -826,10 +851,25 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 			const uint16_t* rows = rows_global + (4 * q) * 16 + c;
 			e0 = __ldcg(rows), e1 = __ldcg(rows + 16), e2 = __ldcg(rows + 32), e3 = __ldcg(rows + 48);
 		}
+#ifdef MOB200_UNPACK_TWO_PASSES
+		// (variant: two copies of the unpack code instead of four)
+		uint4 pa = make_uint4(0, 0, 0, 0), pb = pa, pc = pa, pd = pa;
+#pragma unroll 1
+		for (int h = 0; h < 2; ++h)
+		{
+			const uint4 x = unpack_group(ring, stage_off, h ? e2 : e0, patch_lut);
+			const uint4 y = unpack_group(ring, stage_off, h ? e3 : e1, patch_lut);
+			if (h == 0)
+				pa = x, pb = y;
+			else
+				pc = x, pd = y;
+		}
+#else
 		uint4 pa = unpack_group(ring, stage_off, e0, patch_lut);
 		uint4 pb = unpack_group(ring, stage_off, e1, patch_lut);
 		uint4 pc = unpack_group(ring, stage_off, e2, patch_lut);
 		uint4 pd = unpack_group(ring, stage_off, e3, patch_lut);
+#endif
 
 		const bool bytes = (channel & 3u) == 0;
 		if (bytes)
@@ -930,7 +970,7 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 		if (last)
 			st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
 		uint32_t v = lane_combine(carry, excl, H);
-		uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
+		uint8_t* col = tile + tile_offset(c * 16, vs, B.tile_pad) + q * 4;
 		// one instruction stream for the three channel modes: a warp whose two lanes differ in mode does not run it twice
 #pragma unroll
 		for (int j = 0; j < 16; ++j)
@@ -1065,6 +1105,8 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 	uint64_t* carry_bar = full + kSlots;
 	uint64_t* empty = carry_bar + kSlots;
 	uint64_t* tile_free = empty + kSlots;
+	uint64_t* tile_done = tile_free + 1;
+	uint32_t tma_uses = 0; // blocks of this unit that left by TMA bulk stores (phase of tile_done)
 
 	const uint32_t lane = tid & 31u;
 	const uint32_t warp_base = tid & ~31u;
@@ -1109,6 +1151,30 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
 				decode_quantum(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
 			++tile_uses;
+
+			if (!kRounds && B.tile_pad == kTilePadTma)
+			{
+				// The tile leaves by TMA bulk stores, one per 16-vertex chunk (the chunks are 16 bytes apart in the tile).
+				// Nobody waits at a barrier: every thread makes its tile words visible to the async proxy and arrives on
+				// `tile_done`; one thread (of a different warp every block) waits for the 128 arrivals, issues the copies,
+				// waits until they have READ the tile and then frees it for the next block on behalf of everybody.
+				fence_proxy_async();
+				release_slot<kRounds>(empty + slot, lane);
+				mbar_arrive(tile_done);
+				if (tid == ((tma_uses & 3u) << 5))
+				{
+					mbar_wait(tile_done, tma_uses & 1u);
+					const uint32_t chunk_bytes = 16u * B.vs;
+					const uint32_t nbytes = B.n * B.vs;
+					for (uint32_t cb = 0, o = 0; o < nbytes; ++cb, o += chunk_bytes)
+						tma_store_bulk(B.out + o, tile + cb * (chunk_bytes + kTilePadTma), min(chunk_bytes, nbytes - o));
+					tma_store_commit();
+					tma_store_wait_read();
+					mbar_arrive_count(tile_free, kDecodeThreads);
+				}
+				++tma_uses;
+				continue;
+			}
 
 			// this warp no longer needs the slot (staging bytes, rows, params, carry)
 			release_slot<kRounds>(empty + slot, lane);
@@ -1188,6 +1254,9 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			i += members;
 		}
 	}
+
+	// (bulk stores this thread issued have been written before it leaves)
+	asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
 #ifdef MOB200_DEBUG_COUNTERS
 	if (tid == 0)

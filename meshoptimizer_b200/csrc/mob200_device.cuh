@@ -44,10 +44,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
 	uint32_t ok;
+#ifdef MOB200_TRYWAIT_HINT
+	// (variant: an explicit suspend-time hint in nanoseconds)
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	             : "=r"(ok)
+	             : "r"(smem_addr(bar)), "r"(parity), "r"((uint32_t)MOB200_TRYWAIT_HINT)
+	             : "memory");
+#else
 	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 	             : "=r"(ok)
 	             : "r"(smem_addr(bar)), "r"(parity)
 	             : "memory");
+#endif
 	return ok != 0;
 }
 
@@ -57,6 +65,28 @@ __device__ __forceinline__ void tma_load_bulk(void* dst_smem, const void* src_gm
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
 	             "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
 	             : "memory");
+}
+
+// 1-D TMA bulk copy shared -> global (SASS: UBLKCP), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_bulk(void* dst_gmem, const void* src_smem, uint32_t bytes)
+{
+	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit()
+{
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// all bulk stores of this thread have finished READING shared memory (the source may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read()
+{
+	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_count(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
 
 __device__ __forceinline__ void fence_proxy_async()
