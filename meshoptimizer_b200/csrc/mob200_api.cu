@@ -38,6 +38,7 @@ struct mob200_Plan
 	std::vector<uint32_t> stream_nblocks, stream_block_base; // per sorted stream
 	bool have_offsets = false;
 	int wide_walk_choice = 0, rounds_choice = 0;
+	bool small_blocks_majority = false;
 	// ring of CUDA-event pairs (before / after the fused walk + decode kernel), one per run, recorded on the
 	// launching stream: per-launch durations can be read back after a timed region without any
 	// synchronisation inside it
@@ -296,6 +297,7 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	// pace and a round only waits longer for its members: measured 5-15% slower at 1024 streams): decode in rounds
 	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && n >= (size_t)8 * plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
 	plan->T.wide_walk = ctx->wide_walk_mode == 2 ? (n < (size_t)2 * resident ? 1u : 0u) : (uint32_t)ctx->wide_walk_mode;
+	plan->small_blocks_majority = small_blocks * 2 > total_blocks;
 	plan->wide_walk_choice = (int)plan->T.wide_walk;
 	plan->rounds_choice = (int)plan->T.rounds;
 	plan->sorted_of_caller.assign(n, 0);
@@ -478,6 +480,9 @@ extern "C" int mob200_plan_run_ex(mob200_Plan* plan, void* cuda_stream, int flag
 		return MOB200_ERR_ARGUMENT; // no sidecar was imported and no serial walk has run yet
 	plan->T.block_mode = block_mode ? 1u : 0u;
 	plan->T.wide_walk = block_mode ? 0u : (uint32_t)plan->wide_walk_choice; // block mode: one walker lane per block
+	// block mode: the walk no longer limits a batch of few streams, so small-vertex blocks go through the rounds form
+	// whenever there are enough BLOCKS to keep the units busy
+	plan->T.rounds = (block_mode && plan->ctx->rounds_mode == 2) ? (plan->small_blocks_majority && plan->T.total_blocks >= 8u * plan->grid ? 1u : 0u) : (uint32_t)plan->rounds_choice;
 	if (block_mode && plan->n)
 		CUDA_TRY(cudaMemsetAsync(plan->T.status, 0, plan->n * sizeof(int32_t), st)); // block mode reports failures only
 	if (!block_mode)

@@ -32,8 +32,7 @@ constexpr uint32_t kRoundBlocks = 4;           // rounds variant: blocks the dec
 constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight
 constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
-constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile (conflict-free column writes)
-constexpr uint32_t kTilePadTma = 16;           // ... of a tile that leaves by TMA bulk stores (the chunks must start on 16-byte boundaries; 2-way conflicts)
+constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
 
 struct BlockParams // written by the producer, read by the decoders after the slot's `full` barrier (80 bytes)
 {
@@ -53,7 +52,7 @@ struct BlockParams // written by the producer, read by the decoders after the sl
 	const uint16_t* rows_global;
 	unsigned long long* lookback; // this block's entries (vs/4 of them); predecessors lie vs/4 entries lower each
 	uint32_t round_members;       // rounds variant: > 0: this block opens a decode round of so many consecutive blocks; 0: it continues one
-	uint32_t tma_out;             // plain form: the tile leaves by TMA bulk stores (no filter, 16-byte aligned destination and size)
+	uint32_t pad;
 };
 
 struct SlotData
@@ -72,13 +71,13 @@ template <bool kRounds>
 struct Lay
 {
 	static constexpr uint32_t kSlots = kRounds ? 8 : 4; // blocks in flight between producer and decoders
-	static constexpr uint32_t kTileBytes = kBlockBytes + (kRounds ? kRoundBlocks * 16 * kTilePad : 16 * kTilePadTma); // one 8 KB block, or up to four smaller ones side by side
+	static constexpr uint32_t kTileBytes = kBlockBytes + (kRounds ? kRoundBlocks : 1) * 16 * kTilePad; // one 8 KB block, or up to four smaller ones side by side
 	static constexpr uint32_t kSmemStage = 0;
 	static constexpr uint32_t kSmemTile = kSmemStage + kStageRingBytes;
 	static constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;            // escape-byte selector table: 16 x 4 bytes
 	static constexpr uint32_t kSmemSlots = kSmemPatch + 64;
-	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free, tile_done
-	static constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 2) * 8;   // producer-private: ring_start[kSlots], ring_len[kSlots]
+	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
+	static constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;   // producer-private: ring_start[kSlots], ring_len[kSlots]
 	static constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
 	static constexpr uint32_t kSmemTotal = (kSmemWalker + 32 * 512 + 6 * 4 * 32 + 16 + 1023) & ~1023u; // one unit
 	static constexpr uint32_t kSmemCta = kSmemTotal * kUnitsPerCta;
@@ -115,9 +114,9 @@ __device__ __forceinline__ uint32_t lane_mask(uint32_t channel)
 
 // output tile: row r (vertex) of vs bytes; every 16-row chunk is displaced by kTilePad bytes so that the
 // 4-byte column writes of the 16 chunks of a lane (16 threads of one warp) fall into different banks
-__device__ __forceinline__ uint32_t tile_offset(uint32_t r, uint32_t vs, uint32_t pad = kTilePad)
+__device__ __forceinline__ uint32_t tile_offset(uint32_t r, uint32_t vs)
 {
-	return r * vs + (r >> 4) * pad;
+	return r * vs + (r >> 4) * kTilePad;
 }
 
 #ifdef MOB200_DEBUG_ENDS
@@ -466,11 +465,6 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						P.lookback = reinterpret_cast<unsigned long long*>(m_look);
 						if (kRounds)
 							P.round_members = round_members;
-#ifndef MOB200_NO_TMA_STORE
-						P.tma_out = (!kRounds && m_filter == MOB200_FILTER_NONE && ((m_out | (unsigned long long)(m_n * vs)) & 15ull) == 0) ? 1u : 0u;
-#else
-						P.tma_out = 0;
-#endif
 
 						fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
 						mbar_expect_tx(full + slot, len);
@@ -772,7 +766,7 @@ __device__ __forceinline__ uint4 unpack_group(
 
 struct BlockRegs
 {
-	uint32_t vs, n, groups, gshift, items, stage_off, rows_off, filter, filter_kind, m_chunk, tile_pad;
+	uint32_t vs, n, groups, gshift, items, stage_off, rows_off, filter, filter_kind, m_chunk;
 	bool first_block;
 	const uint16_t* rows_global;
 	uint8_t* out;
@@ -791,7 +785,6 @@ __device__ __forceinline__ BlockRegs load_block(const SlotData& S)
 	B.rows_global = S.P.rows_global;
 	B.out = S.P.out;
 	B.lookback = S.P.lookback;
-	B.tile_pad = S.P.tma_out ? kTilePadTma : kTilePad;
 	return B;
 }
 
@@ -851,8 +844,26 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 			const uint16_t* rows = rows_global + (4 * q) * 16 + c;
 			e0 = __ldcg(rows), e1 = __ldcg(rows + 16), e2 = __ldcg(rows + 32), e3 = __ldcg(rows + 48);
 		}
-#ifdef MOB200_UNPACK_TWO_PASSES
-		// (variant: two copies of the unpack code instead of four)
+#if defined(MOB200_UNPACK_ONE_COPY)
+		// (variant: one copy of the unpack code, four passes)
+		uint4 pa = make_uint4(0, 0, 0, 0), pb = pa, pc = pa, pd = pa;
+#pragma unroll 1
+		for (int h = 0; h < 4; ++h)
+		{
+			const uint4 x = unpack_group(ring, stage_off, h == 0 ? e0 : (h == 1 ? e1 : (h == 2 ? e2 : e3)), patch_lut);
+			if (h == 0)
+				pa = x;
+			else if (h == 1)
+				pb = x;
+			else if (h == 2)
+				pc = x;
+			else
+				pd = x;
+		}
+#elif !defined(MOB200_UNPACK_FOUR_COPIES)
+		// two passes over two copies of the unpack code: the pair of a pass still interleaves, and the hot code of the
+		// three roles, which share the SM's instruction cache, is 4.9 KB smaller than with four copies (measured r2:
+		// 1.583 -> 1.559 ms serial, 1.686 -> 1.656 ms block mode; ONE copy in four passes loses the interleaving: 2.09 ms)
 		uint4 pa = make_uint4(0, 0, 0, 0), pb = pa, pc = pa, pd = pa;
 #pragma unroll 1
 		for (int h = 0; h < 2; ++h)
@@ -970,7 +981,7 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 		if (last)
 			st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
 		uint32_t v = lane_combine(carry, excl, H);
-		uint8_t* col = tile + tile_offset(c * 16, vs, B.tile_pad) + q * 4;
+		uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
 		// one instruction stream for the three channel modes: a warp whose two lanes differ in mode does not run it twice
 #pragma unroll
 		for (int j = 0; j < 16; ++j)
@@ -1105,8 +1116,6 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 	uint64_t* carry_bar = full + kSlots;
 	uint64_t* empty = carry_bar + kSlots;
 	uint64_t* tile_free = empty + kSlots;
-	uint64_t* tile_done = tile_free + 1;
-	uint32_t tma_uses = 0; // blocks of this unit that left by TMA bulk stores (phase of tile_done)
 
 	const uint32_t lane = tid & 31u;
 	const uint32_t warp_base = tid & ~31u;
@@ -1151,30 +1160,6 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
 				decode_quantum(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
 			++tile_uses;
-
-			if (!kRounds && B.tile_pad == kTilePadTma)
-			{
-				// The tile leaves by TMA bulk stores, one per 16-vertex chunk (the chunks are 16 bytes apart in the tile).
-				// Nobody waits at a barrier: every thread makes its tile words visible to the async proxy and arrives on
-				// `tile_done`; one thread (of a different warp every block) waits for the 128 arrivals, issues the copies,
-				// waits until they have READ the tile and then frees it for the next block on behalf of everybody.
-				fence_proxy_async();
-				release_slot<kRounds>(empty + slot, lane);
-				mbar_arrive(tile_done);
-				if (tid == ((tma_uses & 3u) << 5))
-				{
-					mbar_wait(tile_done, tma_uses & 1u);
-					const uint32_t chunk_bytes = 16u * B.vs;
-					const uint32_t nbytes = B.n * B.vs;
-					for (uint32_t cb = 0, o = 0; o < nbytes; ++cb, o += chunk_bytes)
-						tma_store_bulk(B.out + o, tile + cb * (chunk_bytes + kTilePadTma), min(chunk_bytes, nbytes - o));
-					tma_store_commit();
-					tma_store_wait_read();
-					mbar_arrive_count(tile_free, kDecodeThreads);
-				}
-				++tma_uses;
-				continue;
-			}
 
 			// this warp no longer needs the slot (staging bytes, rows, params, carry)
 			release_slot<kRounds>(empty + slot, lane);
@@ -1254,9 +1239,6 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			i += members;
 		}
 	}
-
-	// (bulk stores this thread issued have been written before it leaves)
-	asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
 #ifdef MOB200_DEBUG_COUNTERS
 	if (tid == 0)

@@ -67,28 +67,6 @@ __device__ __forceinline__ void tma_load_bulk(void* dst_smem, const void* src_gm
 	             : "memory");
 }
 
-// 1-D TMA bulk copy shared -> global (SASS: UBLKCP), tracked by the issuing thread's bulk async-group
-__device__ __forceinline__ void tma_store_bulk(void* dst_gmem, const void* src_smem, uint32_t bytes)
-{
-	asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void tma_store_commit()
-{
-	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-
-// all bulk stores of this thread have finished READING shared memory (the source may be overwritten)
-__device__ __forceinline__ void tma_store_wait_read()
-{
-	asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_count(uint64_t* bar, uint32_t count)
-{
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-}
-
 __device__ __forceinline__ void fence_proxy_async()
 {
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -79,7 +79,6 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 				mbar_init(bars + 2 * kSlots + k, kRounds ? kDecodeThreads : kDecodeThreads / 32); // empty: one arrival per decoder warp (plain form) or thread (rounds form)
 			}
 			mbar_init(bars + 3 * kSlots, kDecodeThreads);        // tile_free: one arrival per decoder thread
-			mbar_init(bars + 3 * kSlots + 1, kDecodeThreads);    // tile_done: one arrival per decoder thread (TMA store path)
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		}
 		__syncthreads();
