@@ -23,9 +23,10 @@ full-output parity check on the device.
             the reference's own SIMD decoder (oracle/_ref, meshopt_decodeVertexBuffer per stream; default and -mavx
             builds, the faster is reported) on all host threads of the box, same streams, outputs pre-faulted
 
-Multi-GPU (torchrun, one rank per GPU): every rank decodes its own shard of independent streams (different vertices
-per rank); no collective is on the data path (NCCL only provides the barrier and the max-over-ranks of the timing).
-scaling = weak.
+Multi-GPU (torchrun, one rank per GPU): the job is N x 64 Mi vertices = N x 1024 independent streams, partitioned over the
+ranks by the library's longest-processing-time rule (meshoptimizer_b200/sharding.py); every rank decodes its own shard;
+no collective is on the data path (NCCL only provides the barrier and the max-over-ranks of the timing).  scaling = weak.
+(One process driving all GPUs of a box: mob200_decode_batch_multi_host, measured by tools/bench_multi.py.)
 """
 from __future__ import annotations
 
@@ -408,7 +409,18 @@ def main():
     host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
     segment, block = headline_shape(args.headline)
     t_gen = time.time()
-    v = gen_vertices(rank * args.verts, args.verts, host_threads)
+    if world == 1:
+        v = gen_vertices(0, args.verts, host_threads)
+    else:
+        # the job is world x verts vertices = world x (verts / segment) independent streams; every rank computes the same
+        # longest-processing-time partition (meshoptimizer_b200/sharding.py: no communication) and builds only its own streams
+        from meshoptimizer_b200.sharding import shard_streams, stream_cost
+
+        per_rank = args.verts // segment
+        costs = [stream_cost(int(segment * 32 * 0.43), segment, 32)] * (world * per_rank)
+        mine = shard_streams(costs, world)[rank]
+        assert len(mine) == per_rank
+        v = np.concatenate([gen_vertices(sid * segment, segment, host_threads) for sid in mine])
     wl = encode_workload(v, 32, segment, args.level, args.version, host_threads, block)
     t_gen = time.time() - t_gen
     n = len(wl["offsets"])

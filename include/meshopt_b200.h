@@ -164,6 +164,17 @@ MESHOPTIMIZER_API int mob200_decode_batch_host(mob200_Context* ctx, mob200_Strea
  * whose streams all carry one are decoded in block mode. */
 MESHOPTIMIZER_API int mob200_decode_batch_host_sidecar(mob200_Context* ctx, mob200_Stream* streams, size_t n, const unsigned int* const* sidecars);
 
+/* ---- several GPUs of one box: streams are independent, nothing is exchanged -------------- */
+
+/* Greedy longest-processing-time partition: costs[i] (algorithmic bytes of stream i) -> rank_of[i] in [0, world). */
+MESHOPTIMIZER_API int mob200_shard_streams(const size_t* costs, size_t n, int world, int* rank_of);
+
+/* mob200_decode_batch_host_sidecar over n_devices GPUs: the batch is partitioned by mob200_shard_streams on
+ * src_size + vertex_count * vertex_size, every device gets its own host thread and context (kept for later calls) and
+ * decodes its shard concurrently.  device_ms (optional, n_devices entries): wall time of each device's shard.
+ * Returns the number of failed streams or MOB200_ERR_*. */
+MESHOPTIMIZER_API int mob200_decode_batch_multi_host(const int* devices, int n_devices, mob200_Stream* streams, size_t n, const unsigned int* const* sidecars, float* device_ms);
+
 /* In-place decode filter on a DEVICE buffer of count elements (asynchronous on cuda_stream).
  * filter is enum mob200_Filter (not NONE); stride rules as the reference asserts them. */
 MESHOPTIMIZER_API int mob200_filter_device(int filter, void* device_buffer, size_t count, size_t stride, void* cuda_stream);
@@ -194,6 +205,43 @@ MESHOPTIMIZER_API float mob200_plan_create_ms(const mob200_Plan* plan);
  * count <= 16.
  * Synchronises the device.  Returns 0 or MOB200_ERR_*. */
 MESHOPTIMIZER_API int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long* out, int count, int reset);
+
+/* ---- 2c. encoder-side helper: the segmenter -----------------------------------------
+ *
+ * Host code for the asset pipeline that feeds the GPU decoder: vertex arrays are encoded in the reference wire format
+ * (reference src/vertexcodec.cpp:1615-1693; every stream made here is a valid input of the unmodified
+ * meshopt_decodeVertexBuffer, and has the size the reference encoder gives it at the same level) as independently
+ * decodable segments, each with its block-offset sidecar (section 2b) -- the two things the decoder's parallelism
+ * comes from.  No CUDA is involved. */
+
+/* Upper bound of the encoded size of one stream (the reference's meshopt_encodeVertexBufferBound, :1748-1768). */
+MESHOPTIMIZER_API size_t mob200_encode_vertex_bound(size_t vertex_count, size_t vertex_size);
+
+/* Encode one stream: version 0 or 1, level 0..3 (meaning as meshopt_encodeVertexBufferLevel, :1615).  sidecar: NULL, or
+ * mob200_sidecar_entries(vertex_count, vertex_size) entries that receive the stream's block offsets.  Returns the encoded
+ * size, 0 if buffer_size is too small or an argument is illegal. */
+MESHOPTIMIZER_API size_t mob200_encode_vertex_buffer(unsigned char* buffer, size_t buffer_size, const void* vertices, size_t vertex_count, size_t vertex_size, int level, int version, unsigned int* sidecar);
+
+typedef struct mob200_Segment
+{
+	size_t first_vertex, vertex_count; /* the vertices this stream holds */
+	size_t offset, size;               /* the stream inside the output blob (offset is a multiple of 16) */
+	size_t sidecar_offset, sidecar_entries; /* its block offsets inside the sidecar array (entries, not bytes) */
+} mob200_Segment;
+
+/* ceil(vertex_count / segment_vertices); segment_vertices 0 = one segment */
+MESHOPTIMIZER_API size_t mob200_segment_count(size_t vertex_count, size_t segment_vertices);
+/* capacities mob200_encode_segments needs: bytes of `out`, entries of `sidecars` */
+MESHOPTIMIZER_API size_t mob200_encode_segments_bound(size_t vertex_count, size_t vertex_size, size_t segment_vertices);
+MESHOPTIMIZER_API size_t mob200_segments_sidecar_entries(size_t vertex_count, size_t vertex_size, size_t segment_vertices);
+
+/* Split a vertex array into segments of segment_vertices vertices and encode each as its own stream on `threads` host
+ * threads (0 = all): streams packed back to back on 16-byte boundaries in `out` (*out_size bytes used), one
+ * mob200_Segment per stream, and (sidecars != NULL) every stream's block offsets.  segments[i] maps directly onto a
+ * mob200_Stream {out + offset, size, dst + first_vertex * vertex_size, vertex_count, vertex_size} and onto the sidecar
+ * pointer sidecars + sidecar_offset.  Returns the number of segments or MOB200_ERR_ARGUMENT. */
+MESHOPTIMIZER_API int mob200_encode_segments(const void* vertices, size_t vertex_count, size_t vertex_size, size_t segment_vertices, int level, int version, int threads,
+    unsigned char* out, size_t out_capacity, size_t* out_size, mob200_Segment* segments, size_t segment_capacity, unsigned int* sidecars, size_t sidecar_capacity);
 
 /* ---- 3. index streams (the other two modes of a compressed glTF bufferView) ---------------------- */
 

@@ -85,6 +85,15 @@ class GltfInfo(ctypes.Structure):
     ]
 
 
+class Segment(ctypes.Structure):
+    """mirror of ``mob200_Segment``"""
+    _fields_ = [
+        ("first_vertex", c_size_t), ("vertex_count", c_size_t),
+        ("offset", c_size_t), ("size", c_size_t),
+        ("sidecar_offset", c_size_t), ("sidecar_entries", c_size_t),
+    ]
+
+
 class Stream(ctypes.Structure):
     """mirror of ``mob200_Stream``"""
     _fields_ = [
@@ -107,6 +116,8 @@ EXPORTS = [
     "mob200_plan_run", "mob200_plan_status", "mob200_plan_launches", "mob200_decode_batch_device",
     "mob200_decode_batch_host", "mob200_decode_batch_host_sidecar", "mob200_filter_device", "mob200_context_sm_count", "mob200_version",
     "mob200_plan_last_timing", "mob200_plan_timing_history", "mob200_plan_debug_counters", "mob200_plan_create_ms",
+    "mob200_encode_vertex_bound", "mob200_encode_vertex_buffer", "mob200_segment_count", "mob200_encode_segments_bound", "mob200_segments_sidecar_entries", "mob200_encode_segments",
+    "mob200_shard_streams", "mob200_decode_batch_multi_host",
     "mob200_sidecar_entries", "mob200_plan_create_sidecar", "mob200_plan_run_ex", "mob200_plan_has_offsets", "mob200_plan_export_sidecar",
     "meshopt_decodeIndexBuffer", "meshopt_decodeIndexVersion", "meshopt_decodeIndexSequence",
     "mob200_decode_index_batch_device", "mob200_decode_index_batch_host",
@@ -155,6 +166,22 @@ def lib() -> ctypes.CDLL:
     L.mob200_plan_last_timing.argtypes = [c_void_p, POINTER(c_float)]
     L.mob200_plan_create_ms.restype = c_float
     L.mob200_plan_create_ms.argtypes = [c_void_p]
+    L.mob200_encode_vertex_bound.restype = c_size_t
+    L.mob200_encode_vertex_bound.argtypes = [c_size_t, c_size_t]
+    L.mob200_encode_vertex_buffer.restype = c_size_t
+    L.mob200_encode_vertex_buffer.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p]
+    L.mob200_segment_count.restype = c_size_t
+    L.mob200_segment_count.argtypes = [c_size_t, c_size_t]
+    L.mob200_encode_segments_bound.restype = c_size_t
+    L.mob200_encode_segments_bound.argtypes = [c_size_t, c_size_t, c_size_t]
+    L.mob200_segments_sidecar_entries.restype = c_size_t
+    L.mob200_segments_sidecar_entries.argtypes = [c_size_t, c_size_t, c_size_t]
+    L.mob200_encode_segments.restype = c_int
+    L.mob200_encode_segments.argtypes = [c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, POINTER(c_size_t), POINTER(Segment), c_size_t, c_void_p, c_size_t]
+    L.mob200_shard_streams.restype = c_int
+    L.mob200_shard_streams.argtypes = [POINTER(c_size_t), c_size_t, c_int, POINTER(c_int)]
+    L.mob200_decode_batch_multi_host.restype = c_int
+    L.mob200_decode_batch_multi_host.argtypes = [POINTER(c_int), c_int, POINTER(Stream), c_size_t, POINTER(c_void_p), POINTER(c_float)]
     L.mob200_sidecar_entries.restype = c_size_t
     L.mob200_sidecar_entries.argtypes = [c_size_t, c_size_t]
     L.mob200_plan_create_sidecar.restype = c_int
@@ -442,6 +469,43 @@ class Plan:
 
 def sidecar_entries(vertex_count: int, vertex_size: int) -> int:
     return int(lib().mob200_sidecar_entries(vertex_count, vertex_size))
+
+
+# ---------------------------------------------------------------------------------------------
+# encoder-side helper: the segmenter (host code, no CUDA; reference src/vertexcodec.cpp:1615-1693)
+# ---------------------------------------------------------------------------------------------
+
+def encode_vertex_buffer(vertices, vertex_count: int, vertex_size: int, level: int = 2, version: int = 1, with_sidecar: bool = False):
+    """``mob200_encode_vertex_buffer``: one reference-format stream -> uint8 array (and its block offsets)"""
+    _check_vertex_size(vertex_size)
+    v = _as_u8(vertices)
+    assert v.size >= vertex_count * vertex_size
+    buf = np.empty(int(lib().mob200_encode_vertex_bound(vertex_count, vertex_size)), dtype=np.uint8)
+    side = np.zeros(max(1, sidecar_entries(vertex_count, vertex_size)), dtype=np.uint32) if with_sidecar else None
+    n = lib().mob200_encode_vertex_buffer(buf.ctypes.data, buf.size, v.ctypes.data if v.size else None, vertex_count, vertex_size, level, version,
+                                          side.ctypes.data if with_sidecar else None)
+    if n == 0:
+        raise RuntimeError("mob200_encode_vertex_buffer failed")
+    out = buf[:n].copy()
+    return (out, side[: sidecar_entries(vertex_count, vertex_size)]) if with_sidecar else out
+
+
+def encode_segments(vertices, vertex_count: int, vertex_size: int, segment_vertices: int, level: int = 2, version: int = 1, threads: int = 0, with_sidecars: bool = True):
+    """``mob200_encode_segments``: (blob uint8, list of Segment, sidecar uint32 array or None)"""
+    _check_vertex_size(vertex_size)
+    v = _as_u8(vertices)
+    assert v.size >= vertex_count * vertex_size
+    L = lib()
+    n = int(L.mob200_segment_count(vertex_count, segment_vertices))
+    blob = np.empty(int(L.mob200_encode_segments_bound(vertex_count, vertex_size, segment_vertices)) + 16, dtype=np.uint8)
+    segs = (Segment * max(n, 1))()
+    side = np.zeros(max(1, int(L.mob200_segments_sidecar_entries(vertex_count, vertex_size, segment_vertices))), dtype=np.uint32) if with_sidecars else None
+    used = c_size_t(0)
+    rc = L.mob200_encode_segments(v.ctypes.data if v.size else None, vertex_count, vertex_size, segment_vertices, level, version, threads,
+                                  blob.ctypes.data, blob.size, ctypes.byref(used), segs, n, side.ctypes.data if with_sidecars else None, side.size if with_sidecars else 0)
+    if rc < 0:
+        raise RuntimeError(f"mob200_encode_segments failed ({rc})")
+    return blob[: used.value], [segs[i] for i in range(n)], side
 
 
 def decode_batch_host(items: Iterable[tuple], ctx: Optional[Context] = None):

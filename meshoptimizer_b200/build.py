@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmeshopt_b200.so")
-SOURCES = ["mob200_kernels.cu", "mob200_api.cu", "mob200_index.cu", "mob200_meshlet.cu", "mob200_gltf.cpp"]
+SOURCES = ["mob200_kernels.cu", "mob200_api.cu", "mob200_index.cu", "mob200_meshlet.cu", "mob200_gltf.cpp", "mob200_encode.cpp"]
 HEADERS = ["mob200_common.h", "mob200_host.h", "mob200_kernels.h", "mob200_filters.cuh", "mob200_device.cuh", "mob200_walker.cuh", "mob200_walker_wide.cuh", "mob200_decoder.cuh", os.path.join("..", "..", "include", "meshopt_b200.h")]
 
 NVCC_FLAGS = [

@@ -19,6 +19,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace mob200;
@@ -916,6 +917,94 @@ extern "C" int mob200_decode_batch_host_sidecar(mob200_Context* ctx, mob200_Stre
 	{
 		streams[i].status = skipped[i] ? MOB200_ERR_ARGUMENT : status[i];
 		failed += streams[i].status != 0;
+	}
+	return failed;
+}
+
+// ------------------------------------------------------------------------------------------------
+// several GPUs of one box: streams are independent, so a batch shards with no exchange step
+// ------------------------------------------------------------------------------------------------
+
+// Greedy longest-processing-time assignment (the same rule as meshoptimizer_b200/sharding.py): streams in order of
+// decreasing cost (ties: lower index first), each to the least loaded rank (ties: lower rank).
+extern "C" int mob200_shard_streams(const size_t* costs, size_t n, int world, int* rank_of)
+{
+	if (world <= 0 || (n && (!costs || !rank_of)))
+		return MOB200_ERR_ARGUMENT;
+	std::vector<size_t> order(n);
+	for (size_t i = 0; i < n; ++i)
+		order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return costs[a] > costs[b]; });
+	std::vector<unsigned long long> load((size_t)world, 0);
+	for (size_t i : order)
+	{
+		int best = 0;
+		for (int r = 1; r < world; ++r)
+			if (load[(size_t)r] < load[(size_t)best])
+				best = r;
+		rank_of[i] = best;
+		load[(size_t)best] += costs[i];
+	}
+	return 0;
+}
+
+extern "C" int mob200_decode_batch_multi_host(const int* devices, int n_devices, mob200_Stream* streams, size_t n, const unsigned int* const* sidecars, float* device_ms)
+{
+	if (!devices || n_devices <= 0 || (n && !streams))
+		return MOB200_ERR_ARGUMENT;
+	// one context per device, created on first use and kept (their staging arenas are what makes a call cheap)
+	static std::mutex mu;
+	static mob200_Context* contexts[64] = {};
+	{
+		std::lock_guard<std::mutex> lock(mu);
+		for (int d = 0; d < n_devices; ++d)
+		{
+			if (devices[d] < 0 || devices[d] >= 64)
+				return MOB200_ERR_ARGUMENT;
+			if (!contexts[devices[d]] && mob200_context_create(&contexts[devices[d]], devices[d]) != 0)
+				return MOB200_ERR_CUDA;
+		}
+	}
+
+	std::vector<size_t> costs(n);
+	for (size_t i = 0; i < n; ++i)
+		costs[i] = (streams[i].src ? streams[i].src_size : 0) + streams[i].vertex_count * streams[i].vertex_size; // algorithmic bytes
+	std::vector<int> rank_of(n, 0);
+	if (mob200_shard_streams(costs.data(), n, n_devices, rank_of.data()))
+		return MOB200_ERR_ARGUMENT;
+
+	std::vector<std::vector<size_t>> mine((size_t)n_devices);
+	for (size_t i = 0; i < n; ++i)
+		mine[(size_t)rank_of[i]].push_back(i);
+
+	std::vector<int> rcs((size_t)n_devices, 0);
+	std::vector<std::thread> threads;
+	for (int d = 0; d < n_devices; ++d)
+		threads.emplace_back([&, d]() {
+			const std::vector<size_t>& idx = mine[(size_t)d];
+			std::vector<mob200_Stream> part(idx.size());
+			std::vector<const unsigned int*> side(idx.size(), nullptr);
+			for (size_t k = 0; k < idx.size(); ++k)
+			{
+				part[k] = streams[idx[k]];
+				if (sidecars)
+					side[k] = sidecars[idx[k]];
+			}
+			const auto t0 = std::chrono::steady_clock::now();
+			rcs[(size_t)d] = mob200_decode_batch_host_sidecar(contexts[devices[d]], part.data(), part.size(), sidecars ? side.data() : nullptr);
+			if (device_ms)
+				device_ms[d] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+			for (size_t k = 0; k < idx.size(); ++k)
+				streams[idx[k]].status = part[k].status;
+		});
+	for (std::thread& t : threads)
+		t.join();
+	int failed = 0;
+	for (int d = 0; d < n_devices; ++d)
+	{
+		if (rcs[(size_t)d] < 0)
+			return rcs[(size_t)d];
+		failed += rcs[(size_t)d];
 	}
 	return failed;
 }

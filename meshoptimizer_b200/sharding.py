@@ -37,3 +37,21 @@ def contiguous_shards(n_streams: int, world_size: int) -> List[range]:
         out.append(range(start, start + cnt))
         start += cnt
     return out
+
+
+def shard_streams_native(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """the same partition computed by the library (``mob200_shard_streams``, used by ``mob200_decode_batch_multi_host``)"""
+    import ctypes
+
+    from . import lib
+
+    n = len(costs)
+    arr = (ctypes.c_size_t * max(n, 1))(*[int(c) for c in costs])
+    rank_of = (ctypes.c_int * max(n, 1))()
+    rc = lib().mob200_shard_streams(arr, n, world_size, rank_of)
+    if rc != 0:
+        raise ValueError("mob200_shard_streams failed")
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    for i in range(n):
+        shards[rank_of[i]].append(i)
+    return shards

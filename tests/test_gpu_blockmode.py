@@ -185,3 +185,20 @@ def test_block_mode_error_streams(mb, checker):
     blob[int(w.offsets[2])] = 0xA2       # version 2 -> -1
     outs, status, plan, guard = device_run(w, runs=0, sidecars=sc, block_runs=1, blob_override=blob)
     assert guard and list(status) == [0, -1, -1, 0]
+
+
+@pytest.mark.parametrize("vs,total,seg,version,level", [(32, 300_000, 65_536, 1, 2), (32, 200_000, 0, 1, 2), (16, 150_000, 4096, 0, 0), (12, 90_000, 0, 1, 3), (8, 70_001, 10_000, 1, 2)])
+def test_segmenter_streams_and_sidecars_decode_on_the_device(mb, vs, total, seg, version, level):
+    """mob200_encode_segments (host) -> streams + sidecars -> block-mode decode, never running the serial walk"""
+    rng = np.random.default_rng(9)
+    words = np.cumsum(rng.integers(-200, 200, (total, vs // 4)), axis=0).astype(np.uint32)
+    v = words.view(np.uint8).reshape(-1)
+    blob, segs, side = mb.encode_segments(v, total, vs, seg, level, version, threads=0)
+    n = len(segs)
+    w = workloads.Workload("segmenter", np.concatenate([blob, np.zeros(32, np.uint8)]),
+                           np.array([s.offset for s in segs], np.uint64), np.array([s.size for s in segs], np.uint64),
+                           np.array([s.vertex_count for s in segs], np.uint64), np.full(n, vs, np.uint32), np.zeros(n, np.int32), source=v)
+    sidecars = [side[s.sidecar_offset : s.sidecar_offset + s.sidecar_entries].copy() for s in segs]
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=sidecars, block_runs=1)
+    assert (status == 0).all() and guard
+    assert np.array_equal(np.concatenate(outs), v)

@@ -21,6 +21,9 @@ def test_lpt_partition_properties():
         assert allidx == list(range(1000))            # every stream exactly once
         loads = [sum(costs[i] for i in s) for s in shards]
         assert max(loads) - min(loads) <= max(costs)   # LPT bound
+        # the library's own partition (used by mob200_decode_batch_multi_host) is the same one
+        from meshoptimizer_b200.sharding import shard_streams_native
+        assert shard_streams_native(costs, world) == shards
     assert [len(r) for r in contiguous_shards(10, 4)] == [3, 3, 2, 2]
     assert shard_streams([], 2) == [[], []]
 
