@@ -77,6 +77,31 @@ def dist_env():
     return rank, world, local
 
 
+def numa_bind(local: int):
+    """Best effort: run this rank's host threads on the NUMA node its GPU hangs off, BEFORE any pinned memory is
+    allocated (pinned pages are placed by first touch), so that the host side of the e2e arm does not cross sockets.
+    Returns a short description for the JSON line."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return f"gpu {local} ({bus}): no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {local} ({bus}): node {node} has no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {local} ({bus}) -> NUMA node {node}, {len(cpus)} CPUs"
+    except Exception as e:  # noqa: BLE001 - diagnostics only
+        return f"not bound ({type(e).__name__})"
+
+
 def headline_shape(name: str):
     """(vertices per stream, block mode)"""
     return {"c2b_sidecar": (1 << 16, True), "c2b": (1 << 16, False), "seg4096": (1 << 12, False), "seg4096_sidecar": (1 << 12, True)}[name]
@@ -380,6 +405,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = numa_bind(local) if world > 1 else "single GPU: not bound"
     if world > 1:
         # NCCL prints its version banner on stdout when NCCL_DEBUG is set: keep stdout for the one JSON line
         sys.stdout.flush()
@@ -406,7 +432,7 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
 
-    host_threads = max(1, (os.cpu_count() or 1) // max(1, world))
+    host_threads = max(1, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 1) // max(1, world)))
     segment, block = headline_shape(args.headline)
     t_gen = time.time()
     if world == 1:
@@ -569,7 +595,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, wl, block), "clocks": clocks, "e2e": e2e, "gpu_launches": int(args.steps * plan_launches),
             "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
-            "notes": {"generation_seconds": t_gen, "plan_create_ms": headline_rec["plan_create_ms"], "parity_all_bytes": headline_rec["parity_all_bytes"],
+            "notes": {"generation_seconds": t_gen, "numa": numa, "plan_create_ms": headline_rec["plan_create_ms"], "parity_all_bytes": headline_rec["parity_all_bytes"],
                       "kernels_per_step": ["decode_kernel (one persistent kernel: walker, producer and decoder warps)"],
                       "configs_key": "every entry: one fused kernel launch per step over the whole workload, device-resident, CUDA events; roofline_frac = algorithmic bytes / mean kernel time / peak; parity_all_bytes = every decoded byte compared on the device with the original vertices"},
         }

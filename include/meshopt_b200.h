@@ -303,6 +303,10 @@ typedef struct mob200_Meshlet
 MESHOPTIMIZER_API int mob200_decode_meshlet_batch_device(mob200_Context* ctx, mob200_Meshlet* meshlets, size_t n, void* cuda_stream);
 MESHOPTIMIZER_API int mob200_decode_meshlet_batch_host(mob200_Context* ctx, mob200_Meshlet* meshlets, size_t n);
 
+/* Diagnostics (environment MOB200_TIMING=1): milliseconds of the decode kernel of the most recent meshlet batch of this
+ * process (CUDA events around the launch), without the descriptor upload and the status read-back. */
+MESHOPTIMIZER_API float mob200_debug_last_kernel_ms(void);
+
 /* ---- 4. glTF bufferView front-end (reference gltf/parsegltf.cpp:561-627, decompressMeshopt) ------ */
 
 enum mob200_GltfMode

@@ -122,7 +122,7 @@ EXPORTS = [
     "meshopt_decodeIndexBuffer", "meshopt_decodeIndexVersion", "meshopt_decodeIndexSequence",
     "mob200_decode_index_batch_device", "mob200_decode_index_batch_host",
     "mob200_gltf_scan", "mob200_gltf_decode_host", "mob200_gltf_decode_device",
-    "meshopt_decodeMeshlet", "meshopt_decodeMeshletRaw", "mob200_decode_meshlet_batch_device", "mob200_decode_meshlet_batch_host",
+    "mob200_debug_last_kernel_ms", "meshopt_decodeMeshlet", "meshopt_decodeMeshletRaw", "mob200_decode_meshlet_batch_device", "mob200_decode_meshlet_batch_host",
 ]
 
 
@@ -219,6 +219,7 @@ def lib() -> ctypes.CDLL:
     L.meshopt_decodeMeshlet.argtypes = [c_void_p, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t]
     L.meshopt_decodeMeshletRaw.restype = c_int
     L.meshopt_decodeMeshletRaw.argtypes = [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t]
+    L.mob200_debug_last_kernel_ms.restype = c_float
     L.mob200_decode_meshlet_batch_device.restype = c_int
     L.mob200_decode_meshlet_batch_device.argtypes = [c_void_p, POINTER(Meshlet), c_size_t, c_void_p]
     L.mob200_decode_meshlet_batch_host.restype = c_int

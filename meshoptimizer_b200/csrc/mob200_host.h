@@ -48,6 +48,24 @@ struct DeviceBuffer
 	}
 };
 
+// stream-ordered scratch that is given back on every path out of a function (error returns included)
+struct AsyncScratch
+{
+	void* ptr = nullptr;
+	cudaStream_t stream = nullptr;
+	~AsyncScratch()
+	{
+		if (ptr)
+			cudaFreeAsync(ptr, stream);
+	}
+	int alloc(size_t bytes, cudaStream_t st)
+	{
+		stream = st;
+		CUDA_TRY(cudaMallocAsync(&ptr, bytes, st));
+		return 0;
+	}
+};
+
 struct PinnedBuffer
 {
 	void* ptr = nullptr;

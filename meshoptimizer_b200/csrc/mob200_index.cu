@@ -320,9 +320,11 @@ int run_index_batch(mob200_Context* ctx, mob200_IndexStream* streams, size_t n, 
 	}
 	if (m)
 	{
-		void* d_desc = nullptr;
+		AsyncScratch scratch; // (freed on every return below)
 		const size_t desc_bytes = m * sizeof(DevIndexStream);
-		CUDA_TRY(cudaMallocAsync(&d_desc, desc_bytes + m * sizeof(int32_t), st));
+		if (scratch.alloc(desc_bytes + m * sizeof(int32_t), st))
+			return MOB200_ERR_CUDA;
+		void* d_desc = scratch.ptr;
 		int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_desc) + desc_bytes);
 		CUDA_TRY(cudaMemcpyAsync(d_desc, host.data(), desc_bytes, cudaMemcpyHostToDevice, st));
 		index_decode_kernel<<<(unsigned)((m + kIndexThreads - 1) / kIndexThreads), kIndexThreads, 0, st>>>(static_cast<const DevIndexStream*>(d_desc), d_status, (uint32_t)m);
@@ -330,7 +332,6 @@ int run_index_batch(mob200_Context* ctx, mob200_IndexStream* streams, size_t n, 
 		std::vector<int32_t> rc(m);
 		CUDA_TRY(cudaMemcpyAsync(rc.data(), d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
-		CUDA_TRY(cudaFreeAsync(d_desc, st));
 		for (size_t k = 0; k < m; ++k)
 			streams[map[k]].status = rc[k];
 	}
@@ -400,8 +401,9 @@ extern "C" int mob200_decode_index_batch_host(mob200_Context* ctx, mob200_IndexS
 	{
 		streams[i].status = dev[i].status;
 		const mob200_IndexStream& s = streams[i];
-		// (like the reference, a failed stream may leave partial output behind)
-		if (index_args_ok(s) && s.src && s.dst)
+		// (only a stream that decoded: the staging area is shared with earlier calls, and a rejected stream leaves
+		// the caller's array untouched, which the reference's "may produce garbage" allows)
+		if (index_args_ok(s) && s.src && s.dst && s.status == 0)
 			memcpy(s.dst, static_cast<uint8_t*>(ctx->h_out.ptr) + out_off[i], s.index_count * s.index_size);
 	}
 	return rc;

@@ -11,6 +11,7 @@
 #include "mob200_host.h"
 
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -111,16 +112,235 @@ __device__ int decode_meshlet(const DevMeshlet& m)
 	return data == bound ? 0 : -3;
 }
 
-__global__ void __launch_bounds__(kMeshletThreads) meshlet_decode_kernel(const DevMeshlet* meshlets, int32_t* status, uint32_t n)
+__global__ void __launch_bounds__(kMeshletThreads) meshlet_decode_kernel_thread(const DevMeshlet* meshlets, int32_t* status, uint32_t n)
 {
+	// (first form: one thread per meshlet; kept for A/B, MOB200_MESHLET_FORM=0)
 	const uint32_t i = blockIdx.x * kMeshletThreads + threadIdx.x;
 	if (i < n)
 		status[i] = decode_meshlet(meshlets[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// second form: EIGHT LANES per meshlet, four meshlets per warp
+// ------------------------------------------------------------------------------------------------
+//
+// Everything that is a prefix sum is done by the eight lanes in parallel: the control bytes are known up front, so
+// the byte offset of every vertex delta (lengths 0-4) and of every triangle's extra bytes (0-3 by its 4-bit code),
+// the running vertex value and the running "next new vertex" counter are segmented warp scans; the lanes fetch
+// their own bytes, finish the vertex references and write them coalesced, and leave one 32-bit descriptor per
+// triangle in shared memory (its literal corners and its code).  What remains serial is the triangle FIFO
+// (a triangle reuses an edge of one of the three before it): one short register-only chain per triangle,
+//   edge = f[code / 4] >> shift;  tri = code < 12 ? edge corners + new corner : literal corners
+// run by the group's lanes in step from the descriptors, so that a warp instruction of the chain serves four
+// meshlets.  The finished triangles go back through shared memory and leave coalesced.  Error checks have the
+// granularity of the reference's x86 path (see the header of this file); offsets only grow, so "some check in front
+// of a group fails" is the same as "the first one fails".
+constexpr int kGroupLanes = 8;
+constexpr int kMeshletsPerCta = kMeshletThreads / kGroupLanes; // 16
+constexpr uint32_t kMaxMeshletBytes = 2048; // a larger buffer cannot end where its data section does (4 * 256 + 3 * 256 + 16 + 64 + 128 = 2000): -3
+
+__device__ __forceinline__ uint32_t load_byte(const uint8_t* src, uint32_t off, uint32_t size)
+{
+	return off < size ? (uint32_t)__ldg(src + off) : 0u; // (a malformed stream may point anywhere: never outside the buffer)
+}
+
+// inclusive scan over the 8 lanes of a group
+__device__ __forceinline__ uint32_t group_scan(uint32_t v, uint32_t gl)
+{
+#pragma unroll
+	for (int d = 1; d < kGroupLanes; d <<= 1)
+	{
+		const uint32_t o = __shfl_up_sync(0xffffffffu, v, d, kGroupLanes);
+		if (gl >= (uint32_t)d)
+			v += o;
+	}
+	return v;
+}
+
+__global__ void __launch_bounds__(kMeshletThreads) meshlet_decode_kernel(const DevMeshlet* meshlets, int32_t* status, uint32_t n)
+{
+	__shared__ uint32_t desc_all[kMeshletsPerCta][256]; // triangle descriptors (parallel part -> chain)
+	__shared__ uint32_t tri_all[kMeshletsPerCta][256];  // finished triangles (chain -> coalesced stores)
+	const uint32_t lane = threadIdx.x & 31u, gl = lane & 7u;
+	const uint32_t group = threadIdx.x / kGroupLanes;
+	const uint32_t idx = blockIdx.x * kMeshletsPerCta + group;
+	const bool have = idx < n;
+	uint32_t* desc = desc_all[group];
+	uint32_t* tris = tri_all[group];
+
+	DevMeshlet m = {};
+	if (have)
+		m = meshlets[idx];
+	const uint8_t* src = m.src;
+	const uint32_t size = m.src_size;
+	const uint32_t vc = m.vertex_count, tc = m.triangle_count;
+	const uint32_t code_bytes = (tc + 1) / 2, ctrl_bytes = (vc + 3) / 4;
+	const uint32_t gap = code_bytes + ctrl_bytes < 16 ? 16 - (code_bytes + ctrl_bytes) : 0;
+	int rc = 0;
+	if (have && size < code_bytes + ctrl_bytes + gap)
+		rc = -2;
+	else if (have && size > kMaxMeshletBytes)
+		rc = -3;
+	const bool run = have && rc == 0;
+	const uint32_t codes = run ? size - code_bytes : 0;
+	const uint32_t ctrl = codes - (run ? ctrl_bytes : 0);
+	const uint32_t bound = ctrl - (run ? gap : 0);
+	const uint32_t vcr = run ? vc : 0, tcr = run ? tc : 0;
+
+	uint32_t data = 0;          // bytes of the data section consumed so far (group-uniform)
+	uint32_t last = 0xffffffffu; // running vertex reference
+	bool overrun = false;
+
+	// ---- vertex references: 32 per pass, four (one control byte) per lane ----------------------------------------------
+	const uint32_t vmax = __reduce_max_sync(0xffffffffu, vcr);
+	for (uint32_t base = 0; base < vmax; base += 32)
+	{
+		const uint32_t i0 = base + gl * 4;
+		const bool on = i0 < vcr;
+		const uint32_t c4 = on ? load_byte(src, ctrl + (i0 >> 2), size) : 0u;
+		uint32_t len[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			len[k] = !on ? 0u : (c4 == 0xffu ? 4u : (((c4 >> k) & 1u) | ((c4 >> (k + 3)) & 2u)));
+		const uint32_t mine = len[0] + len[1] + len[2] + len[3];
+		const uint32_t incl = group_scan(mine, gl);
+		uint32_t off = data + incl - mine;
+		overrun |= on && off > bound;
+		uint32_t delta[4], dsum = 0;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t v = 0;
+#pragma unroll
+			for (uint32_t j = 0; j < 4; ++j)
+				if (j < len[k])
+					v |= load_byte(src, off + j, size) << (8 * j);
+			off += len[k];
+			delta[k] = on ? ((v >> 1) ^ (0u - (v & 1u))) + 1u : 0u;
+			dsum += delta[k];
+		}
+		const uint32_t dincl = group_scan(dsum, gl);
+		uint32_t value = last + dincl - dsum;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			value += delta[k];
+			if (i0 + k < vcr)
+			{
+				if (m.vertex_size == 4)
+					reinterpret_cast<uint32_t*>(m.vertices)[i0 + k] = value;
+				else
+					reinterpret_cast<uint16_t*>(m.vertices)[i0 + k] = (uint16_t)value;
+			}
+		}
+		data += __shfl_sync(0xffffffffu, incl, 7, kGroupLanes);
+		last += __shfl_sync(0xffffffffu, dincl, 7, kGroupLanes);
+	}
+
+	// ---- triangles, parallel part: offsets of the extra bytes, new-vertex numbers, one descriptor per triangle -------------
+	// descriptor = c | a << 8 | b << 16 | code << 24 (a, b only for the literal codes 12..15)
+	const uint32_t check_mask = m.triangle_size == 3 ? 3u : 1u; // byte triangles are checked four at a time, packed ones in pairs
+	const uint32_t tmax = __reduce_max_sync(0xffffffffu, tcr);
+	uint32_t next = 0;
+	for (uint32_t base = 0; base < tmax; base += 32)
+	{
+		const uint32_t t0 = base + gl * 4;
+		uint32_t code[4], nbytes = 0, nnew = 0;
+		const uint32_t cb0 = t0 < tcr ? load_byte(src, codes + (t0 >> 1), size) : 0u;
+		const uint32_t cb1 = t0 + 2 < tcr ? load_byte(src, codes + (t0 >> 1) + 1, size) : 0u;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			code[k] = ((k < 2 ? cb0 : cb1) >> ((k & 1) * 4)) & 15u;
+			if (t0 + k < tcr)
+			{
+				const uint32_t extra = code[k] < 12 ? (code[k] & 1u) : code[k] - 12u; // bytes taken from the data section
+				nbytes += extra;
+				nnew += (code[k] < 12 ? 1u : 3u) - extra;                             // corners numbered by the running counter
+			}
+		}
+		const uint32_t bincl = group_scan(nbytes, gl), nincl = group_scan(nnew, gl);
+		uint32_t off = data + bincl - nbytes, nx = next + nincl - nnew;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			const uint32_t t = t0 + k;
+			if (t < tcr)
+			{
+				if ((t & check_mask) == 0 && off > bound)
+					overrun = true;
+				const uint32_t cd = code[k];
+				uint32_t a = 0, b = 0, c;
+				if (cd < 12)
+					c = (cd & 1u) ? load_byte(src, off++, size) : (nx++ & 0xffu);
+				else
+				{
+					a = cd > 12 ? load_byte(src, off++, size) : (nx++ & 0xffu);
+					b = cd > 13 ? load_byte(src, off++, size) : (nx++ & 0xffu);
+					c = cd > 14 ? load_byte(src, off++, size) : (nx++ & 0xffu);
+				}
+				desc[t] = c | (a << 8) | (b << 16) | (cd << 24);
+			}
+		}
+		data += __shfl_sync(0xffffffffu, bincl, 7, kGroupLanes);
+		next += __shfl_sync(0xffffffffu, nincl, 7, kGroupLanes);
+	}
+	__syncwarp();
+
+	// ---- triangles, serial part: the FIFO of the last three triangles (packed c | a << 8 | b << 16 | c << 24) ------------
+	// every lane of the group runs the same chain; lane t % 8 keeps triangle t
+	{
+		uint32_t f0 = 0, f1 = 0, f2 = 0;
+		for (uint32_t t = 0; t < tmax; ++t)
+		{
+			const uint32_t d = t < tcr ? desc[t] : 0u;
+			const uint32_t cd = d >> 24, c = d & 0xffu;
+			uint32_t edge = cd < 4 ? f0 : (cd < 8 ? f1 : f2);
+			edge >>= (cd << 3) & 16u;
+			const uint32_t reuse = ((edge & 0xffu) << 16) | (edge & 0xff00u) | c | (c << 24);
+			const uint32_t lit = (d & 0x00ffffffu) | (c << 24);
+			const uint32_t tri = cd < 12 ? reuse : lit;
+			f2 = f1;
+			f1 = f0;
+			f0 = tri;
+			if (t < tcr && (t & 7u) == gl)
+				tris[t] = tri;
+		}
+	}
+	__syncwarp();
+
+	// ---- triangles out, coalesced -------------------------------------------------------------------------------------------
+	if (m.triangle_size == 4)
+	{
+		for (uint32_t t = gl; t < tcr; t += kGroupLanes)
+			reinterpret_cast<uint32_t*>(m.triangles)[t] = tris[t] >> 8;
+	}
+	else
+	{
+		for (uint32_t o = gl; o < tcr * 3; o += kGroupLanes)
+		{
+			const uint32_t t = o / 3, comp = o - t * 3;
+			m.triangles[o] = (uint8_t)(tris[t] >> (8 + 8 * comp));
+		}
+	}
+
+	// the overrun flag of a meshlet is the OR over its eight lanes
+	const uint32_t ballot = __ballot_sync(0xffffffffu, overrun);
+	const bool group_overrun = ((ballot >> (lane & 24u)) & 0xffu) != 0;
+	if (have && gl == 0)
+		status[idx] = rc != 0 ? rc : (group_overrun ? -2 : (data == bound ? 0 : -3));
+}
+
 } // namespace mob200
 
 using namespace mob200;
+
+static float g_last_kernel_ms = 0.f;
+
+extern "C" float mob200_debug_last_kernel_ms(void)
+{
+	return g_last_kernel_ms;
+}
 
 namespace
 {
@@ -172,17 +392,38 @@ int run_meshlet_batch(mob200_Meshlet* meshlets, size_t n, cudaStream_t st)
 	const size_t cnt = host.size();
 	if (cnt)
 	{
-		void* d_desc = nullptr;
+		AsyncScratch scratch; // (freed on every return below)
 		const size_t desc_bytes = cnt * sizeof(DevMeshlet);
-		CUDA_TRY(cudaMallocAsync(&d_desc, desc_bytes + cnt * sizeof(int32_t), st));
+		if (scratch.alloc(desc_bytes + cnt * sizeof(int32_t), st))
+			return MOB200_ERR_CUDA;
+		void* d_desc = scratch.ptr;
 		int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_desc) + desc_bytes);
 		CUDA_TRY(cudaMemcpyAsync(d_desc, host.data(), desc_bytes, cudaMemcpyHostToDevice, st));
-		meshlet_decode_kernel<<<(unsigned)((cnt + kMeshletThreads - 1) / kMeshletThreads), kMeshletThreads, 0, st>>>(static_cast<const DevMeshlet*>(d_desc), d_status, (uint32_t)cnt);
+		static const int form = getenv("MOB200_MESHLET_FORM") ? atoi(getenv("MOB200_MESHLET_FORM")) : 1;
+		static const bool timing = getenv("MOB200_TIMING") != nullptr; // diagnostics: kernel time of the last batch (mob200_debug_last_kernel_ms)
+		cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+		if (timing)
+		{
+			cudaEventCreate(&ev0);
+			cudaEventCreate(&ev1);
+			cudaEventRecord(ev0, st);
+		}
+		if (form == 0)
+			meshlet_decode_kernel_thread<<<(unsigned)((cnt + kMeshletThreads - 1) / kMeshletThreads), kMeshletThreads, 0, st>>>(static_cast<const DevMeshlet*>(d_desc), d_status, (uint32_t)cnt);
+		else
+			meshlet_decode_kernel<<<(unsigned)((cnt + kMeshletsPerCta - 1) / kMeshletsPerCta), kMeshletThreads, 0, st>>>(static_cast<const DevMeshlet*>(d_desc), d_status, (uint32_t)cnt);
 		CUDA_TRY(cudaGetLastError());
+		if (timing)
+			cudaEventRecord(ev1, st);
 		std::vector<int32_t> rc(cnt);
 		CUDA_TRY(cudaMemcpyAsync(rc.data(), d_status, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(cudaStreamSynchronize(st));
-		CUDA_TRY(cudaFreeAsync(d_desc, st));
+		if (timing)
+		{
+			cudaEventElapsedTime(&g_last_kernel_ms, ev0, ev1);
+			cudaEventDestroy(ev0);
+			cudaEventDestroy(ev1);
+		}
 		for (size_t k = 0; k < cnt; ++k)
 			meshlets[map[k]].status = rc[k];
 	}
@@ -259,7 +500,9 @@ extern "C" int mob200_decode_meshlet_batch_host(mob200_Context* ctx, mob200_Mesh
 	{
 		meshlets[i].status = dev[i].status;
 		const mob200_Meshlet& m = meshlets[i];
-		if (!meshlet_args_ok(m) || !m.src)
+		// (only a meshlet that decoded: the staging area is shared with earlier calls, and a rejected meshlet leaves
+		// the caller's arrays untouched)
+		if (!meshlet_args_ok(m) || !m.src || m.status != 0)
 			continue;
 		if (m.vertex_count)
 			memcpy(m.vertices, static_cast<uint8_t*>(ctx->h_out.ptr) + v_off[i], m.vertex_count * m.vertex_size);
