@@ -532,6 +532,52 @@ def main():
             measure(f"c1a_grid_v{ver}_sidecar", wg, True, 10, 3, exp=gexp, verts=grid.size // 32, outbuf=gout)
         del gexp, gout
 
+    # ---- C3: gltfpack-style filtered streams (BASELINE configs[2]), decode + FUSED filter, SURVEY Appendix D shapes -------
+    c3_table = None
+    if world == 1 and not args.no_configs:
+        from oracle import workloads
+
+        c3_table = []
+        P = loader.port()
+        for kind in workloads.C3_KINDS:
+            w3 = workloads.c3(kind, count=1 << 24, seg=1 << 16, version=1, level=2)
+            want = torch.from_numpy(np.concatenate(workloads.expected_outputs(w3))).to(dev)
+            vs3 = int(w3.vertex_sizes[0])
+            sc3 = [P.block_offsets(int(w3.counts[i]), vs3, w3.stream(i))[1] for i in range(w3.n)]
+            wl3 = dict(blob=w3.blob, offsets=w3.offsets, sizes=w3.sizes, counts=w3.counts, vs=vs3, segment=1 << 16, level=2, version=1,
+                       decoded_bytes=w3.decoded_bytes, encoded_bytes=w3.encoded_bytes, sidecars=sc3, sidecar_bytes=int(sum(x.size for x in sc3)) * 4)
+            o3 = torch.zeros(w3.decoded_bytes + 64, dtype=torch.uint8, device=dev)
+            for blk in (False, True):
+                n3 = w3.n
+                offs3 = np.zeros(n3, np.uint64)
+                np.cumsum((w3.counts * np.uint64(vs3))[:-1], out=offs3[1:])
+                blob3 = torch.from_numpy(w3.blob).to(dev)
+                items3 = [(blob3.data_ptr() + int(w3.offsets[i]), int(w3.sizes[i]), o3.data_ptr() + int(offs3[i]), int(w3.counts[i]), vs3, int(w3.filters[i])) for i in range(n3)]
+                plan3 = mb.Plan(ctx, mb.make_streams(items3), sidecars=sc3 if blk else None)
+                o3.zero_()
+                plan3.run(stream, block_parallel=blk)
+                st3 = plan3.status(stream)
+                got = o3[: w3.decoded_bytes]
+                if vs3 == 4 and w3.meta["filter_name"] in ("oct", "color"):  # the two lanes with a stated <= 1 LSB tolerance
+                    dd = (got.to(torch.int16) - want.to(torch.int16)).abs()
+                    ok3 = bool((torch.minimum(dd, 256 - dd) <= 1).all())
+                else:
+                    ok3 = bool(torch.equal(got, want))
+                for _ in range(3):
+                    plan3.run(stream, block_parallel=blk)
+                for _ in range(8):
+                    plan3.run(stream, block_parallel=blk)
+                torch.cuda.synchronize()
+                kms = float(np.min(plan3.timing_history(8)))
+                alg3 = w3.encoded_bytes + w3.decoded_bytes + (wl3["sidecar_bytes"] if blk else 0)
+                c3_table.append({"kind": kind, "filter": w3.meta["filter_name"], "vertex_size": vs3, "streams": n3, "elements": int(w3.counts.sum()),
+                                 "mode": "block (sidecar)" if blk else "serial walk", "kernel_ms_best": kms, "decoded_GBps": w3.decoded_bytes / kms / 1e6,
+                                 "traffic_GBps": alg3 / kms / 1e6, "roofline_frac": alg3 / kms / 1e6 / peak, "parity": bool(ok3 and (st3 == 0).all()),
+                                 "tolerance": "<= 1 LSB" if vs3 == 4 and w3.meta["filter_name"] in ("oct", "color") else "bit-exact"})
+                del plan3, blob3
+            del o3, want
+            torch.cuda.empty_cache()
+
     # ---- end-to-end arm: host buffers through the C ABI ---------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -594,7 +640,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, wl, block), "clocks": clocks, "e2e": e2e, "gpu_launches": int(args.steps * plan_launches),
-            "roofline": roofline, "cpu_baseline": cpu, "configs": configs,
+            "roofline": roofline, "cpu_baseline": cpu, "configs": configs, "c3_fused_filters": c3_table,
             "notes": {"generation_seconds": t_gen, "numa": numa, "plan_create_ms": headline_rec["plan_create_ms"], "parity_all_bytes": headline_rec["parity_all_bytes"],
                       "kernels_per_step": ["decode_kernel (one persistent kernel: walker, producer and decoder warps)"],
                       "configs_key": "every entry: one fused kernel launch per step over the whole workload, device-resident, CUDA events; roofline_frac = algorithmic bytes / mean kernel time / peak; parity_all_bytes = every decoded byte compared on the device with the original vertices"},
