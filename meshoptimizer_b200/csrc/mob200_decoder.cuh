@@ -527,7 +527,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				}
 				if (kBlock && valid && !carry_done && b > 0 && nq <= 32)
 				{
-					// Decoupled look-back, 32 / nqp predecessors per step (nqp = nq rounded up to a power of two): lane =
+					// Decoupled look-back, 2 * 32 / nqp predecessors per step (nqp = nq rounded up to a power of two): lane =
 					// (predecessor pj, 4-byte lane q).  Per q the lanes consume the leading run of published predecessors up
 					// to the first inclusive prefix (state 2), combine their values with a butterfly over pj, and go on
 					// behind that run until a prefix has been met.  (Block 0 of a stream only ever publishes a prefix, so
@@ -540,25 +540,42 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 					const bool qon = q < nq;
 					const uint32_t Hq = lane_mask(qon ? S.channels[q] : 0u);
 					const uint32_t want_epoch = T.epoch & 0x3fffffffu;
+					// every lane looks at TWO consecutive predecessors per step (one when nqp == 1: 32 lanes = 32 predecessors
+					// already): predecessor slot 2 * pj + h sits at bit pj * nqp + h * nqp / 2 of the masks, i.e. in order of distance
+					const bool two = nqp >= 2;
+					const uint32_t half = nqp >> 1, per = two ? 2u : 1u;
+					const uint32_t slots = two ? (pattern | (pattern << half)) : pattern;
 					bool done = !qon;
 					uint32_t acc = 0, dist = 1;
 					while (!__all_sync(0xffffffffu, done))
 					{
-						const bool here = !done && dist + pj <= b;
-						unsigned long long e = 0;
-						if (here)
-							e = ld_volatile_u64(look + q - (size_t)(dist + pj) * nq);
-						const uint32_t flag = (uint32_t)(e >> 32);
-						const uint32_t state = here ? ((flag >> 2) == want_epoch ? (flag & 3u) : 0u) : 2u; // (beyond block 0: never reached)
-						const uint32_t rmask = (__ballot_sync(0xffffffffu, state != 0) >> q) & pattern;
-						const uint32_t pmask = (__ballot_sync(0xffffffffu, state == 2) >> q) & pattern;
-						const uint32_t nr = ~rmask & pattern;                        // predecessors that have not published yet
+						const uint32_t d0 = dist + per * pj, d1 = d0 + 1u;
+						const bool here0 = !done && d0 <= b, here1 = two && !done && d1 <= b;
+						unsigned long long e0 = 0, e1 = 0;
+						if (here0)
+							e0 = ld_volatile_u64(look + q - (size_t)d0 * nq);
+						if (here1)
+							e1 = ld_volatile_u64(look + q - (size_t)d1 * nq);
+						const uint32_t f0 = (uint32_t)(e0 >> 32), f1 = (uint32_t)(e1 >> 32);
+						// (beyond block 0: "prefix 0", never reached because block 0 itself is a prefix)
+						const uint32_t s0 = here0 ? ((f0 >> 2) == want_epoch ? (f0 & 3u) : 0u) : 2u;
+						const uint32_t s1 = here1 ? ((f1 >> 2) == want_epoch ? (f1 & 3u) : 0u) : 2u;
+						uint32_t rmask = (__ballot_sync(0xffffffffu, s0 != 0) >> q) & pattern;
+						uint32_t pmask = (__ballot_sync(0xffffffffu, s0 == 2) >> q) & pattern;
+						if (two)
+						{
+							rmask |= ((__ballot_sync(0xffffffffu, s1 != 0) >> q) & pattern) << half;
+							pmask |= ((__ballot_sync(0xffffffffu, s1 == 2) >> q) & pattern) << half;
+						}
+						const uint32_t nr = ~rmask & slots;                                // predecessors that have not published yet
 						const uint32_t below = nr ? ((nr & (0u - nr)) - 1u) : 0xffffffffu; // ... and everything nearer than the first of them
-						const uint32_t fp = (pmask & below) & (0u - (pmask & below)); // nearest inclusive prefix inside that run
-						uint32_t consume = below & pattern;
+						const uint32_t fp = (pmask & below) & (0u - (pmask & below));      // nearest inclusive prefix inside that run
+						uint32_t consume = below & slots;
 						if (fp)
 							consume &= (fp << 1) - 1u;
-						uint32_t v = (!done && ((consume >> (pj * nqp)) & 1u)) ? (uint32_t)e : 0u;
+						uint32_t v = (!done && ((consume >> (pj * nqp)) & 1u)) ? (uint32_t)e0 : 0u;
+						if (two && !done && ((consume >> (pj * nqp + half)) & 1u))
+							v = lane_combine(v, (uint32_t)e1, Hq);
 						for (uint32_t st = nqp; st < 32; st <<= 1)
 							v = lane_combine(v, __shfl_xor_sync(0xffffffffu, v, st), Hq);
 						if (!done)
@@ -569,7 +586,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 							else
 								dist += __popc(consume);
 							if (consume == 0)
-								__nanosleep(100);
+								__nanosleep(64);
 						}
 					}
 					if (qon && pj == 0)
