@@ -40,6 +40,7 @@ struct mob200_Plan
 	bool have_offsets = false;
 	int wide_walk_choice = 0, rounds_choice = 0;
 	bool small_blocks_majority = false;
+	bool two_phase = false; // the last run was a team walk + block-mode decode (two launches)
 	// ring of CUDA-event pairs (before / after the fused walk + decode kernel), one per run, recorded on the
 	// launching stream: per-launch durations can be read back after a timed region without any
 	// synchronisation inside it
@@ -76,6 +77,8 @@ extern "C" int mob200_context_create(mob200_Context** out, int device)
 	CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	if (const char* wide = getenv("MOB200_WIDE_WALK"))
 		ctx->wide_walk_mode = atoi(wide);
+	if (const char* team = getenv("MOB200_TEAM_WALK"))
+		ctx->team_walk = atoi(team);
 	if (const char* rounds = getenv("MOB200_ROUNDS"))
 		ctx->rounds_mode = atoi(rounds);
 	if (const char* lead = getenv("MOB200_WALKER_LEAD"))
@@ -388,7 +391,11 @@ extern "C" void mob200_plan_destroy(mob200_Plan* plan)
 
 extern "C" int mob200_plan_launches(const mob200_Plan* plan)
 {
-	return (plan && plan->n) ? 1 : 0; // one fused persistent kernel per run
+	if (!plan || !plan->n)
+		return 0;
+	// one fused persistent kernel per run; plans of few long streams run the offsets-only team walk in front of it
+	const bool two_phase = plan->runs ? plan->two_phase : (plan->wide_walk_choice == 1 && plan->ctx->team_walk && plan->T.walker_lead == 0);
+	return two_phase ? 2 : 1;
 }
 
 extern "C" int mob200_plan_create_sidecar(mob200_Context* ctx, const mob200_Stream* streams, size_t n, const unsigned int* const* sidecars, mob200_Plan** out)
@@ -451,7 +458,7 @@ struct DeviceSerial
 };
 static DeviceSerial g_serial[64];
 
-static int launch_serialised(const mob200_Context* ctx, const DevTables& T, uint32_t ctas, cudaStream_t st, cudaEvent_t before, cudaEvent_t after)
+static int launch_serialised(const mob200_Context* ctx, const DevTables& T, uint32_t ctas, cudaStream_t st, cudaEvent_t before, cudaEvent_t after, const DevTables* team_walk)
 {
 	DeviceSerial& ds = g_serial[ctx->device & 63];
 	std::lock_guard<std::mutex> lock(ds.mu);
@@ -461,6 +468,8 @@ static int launch_serialised(const mob200_Context* ctx, const DevTables& T, uint
 		CUDA_TRY(cudaStreamWaitEvent(st, ds.last, 0));
 	if (before)
 		CUDA_TRY(cudaEventRecord(before, st));
+	if (team_walk)
+		CUDA_TRY(launch_walk_team(*team_walk, ctx->sm_count, st)); // phase 1 on its own: block offsets and return codes
 	CUDA_TRY(launch_decode(T, ctas, st));
 	if (after)
 		CUDA_TRY(cudaEventRecord(after, st));
@@ -498,13 +507,27 @@ extern "C" int mob200_plan_run_ex(mob200_Plan* plan, void* cuda_stream, int flag
 	DevTables T = plan->T;
 	if (reuse_tables && plan->runs == 0)
 		T.walker_lead = 0; // the first run builds the tables
+	// Few long streams (the plans that used to take the one-warp-per-stream walker): the offsets-only team walk fills the
+	// block-offset table and the status words, then every block is walked and decoded in block mode.
+	DevTables Twalk = {};
+	const bool two_phase = !block_mode && plan->wide_walk_choice == 1 && plan->ctx->team_walk && plan->T.walker_lead == 0 && plan->n > 0;
+	if (two_phase)
+	{
+		Twalk = T;
+		T.block_mode = 1;
+		T.wide_walk = 0;
+		T.keep_status = 1;
+		if (plan->ctx->rounds_mode == 2)
+			T.rounds = plan->small_blocks_majority && plan->T.total_blocks >= 8u * plan->grid ? 1u : 0u;
+	}
+	plan->two_phase = two_phase;
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
 	const bool timed = ev[0] != nullptr;
 	// unit u runs in CTA u % ctas: a batch with few units still spreads over all SMs
 	const uint32_t ctas_max = (uint32_t)(plan->ctx->sm_count * plan->ctx->decode_ctas_per_sm);
 	const uint32_t ctas = std::max<uint32_t>((plan->grid + kUnitsPerCta - 1) / kUnitsPerCta, std::min<uint32_t>(ctas_max, plan->grid));
-	if (launch_serialised(plan->ctx, T, ctas, st, timed ? ev[0] : nullptr, timed ? ev[1] : nullptr))
+	if (launch_serialised(plan->ctx, T, ctas, st, timed ? ev[0] : nullptr, timed ? ev[1] : nullptr, two_phase ? &Twalk : nullptr))
 		return MOB200_ERR_CUDA;
 	plan->runs++;
 	return 0;

@@ -94,6 +94,8 @@ struct DevTables
 	uint32_t block_mode;          // 1: block_offset is an INPUT (a block-offset sidecar: caller-provided, or kept from an earlier run):
 	                              // every block is walked on its own by one walker lane, which also checks that the block ends where
 	                              // the next one is said to start -- a stale sidecar is detected, never trusted (kStatusSidecar)
+	uint32_t keep_status;         // block mode after the team walk: the status words already hold the reference codes; only a
+	                              // stream that is still 0 may be marked kStatusSidecar
 };
 
 constexpr int32_t kStatusSidecar = -102; // = MOB200_ERR_SIDECAR (include/meshopt_b200.h)

@@ -29,6 +29,7 @@
 #include "mob200_filters.cuh"
 #include "mob200_walker.cuh"
 #include "mob200_walker_wide.cuh"
+#include "mob200_walk_team.cuh"
 
 namespace mob200
 {
@@ -310,6 +311,17 @@ cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream
 		else
 			decode_kernel<false, false, false><<<grid, kCtaThreads, Lay<false>::kSmemCta, stream>>>(T);
 	}
+	return cudaGetLastError();
+}
+
+cudaError_t launch_walk_team(const DevTables& T, int sm_count, cudaStream_t stream)
+{
+	if (T.n_streams == 0)
+		return cudaSuccess;
+	// one CTA per stream, at most what the device holds at once (the rest by grid stride)
+	const uint32_t cap = (uint32_t)sm_count * 7u;
+	const uint32_t grid = T.n_streams < cap ? T.n_streams : cap;
+	walk_team_kernel<<<grid, kTeamThreads, kTeamSmemBytes, stream>>>(T);
 	return cudaGetLastError();
 }
 

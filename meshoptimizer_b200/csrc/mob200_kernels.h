@@ -40,6 +40,8 @@ cudaError_t prepare_decode_kernel();
 cudaError_t decode_occupancy(int* ctas_per_sm);
 
 cudaError_t launch_decode(const DevTables& T, uint32_t grid, cudaStream_t stream);
+// few long streams: offsets-only walk, one CTA (chain warp + helper warps) per stream; followed by a block-mode launch_decode
+cudaError_t launch_walk_team(const DevTables& T, int sm_count, cudaStream_t stream);
 cudaError_t launch_filter(int filter, void* data, size_t count, size_t stride, int sm_count, cudaStream_t stream);
 
 } // namespace mob200

@@ -506,8 +506,17 @@ __device__ void walk_group(const DevTables& T, WalkWarp& W, uint32_t base, uint3
 			for (uint32_t b = b_first + done; b < b_first + b_count; ++b)
 				st_release_u32(ready + b, ready_word(T.epoch, 0, false)); // nothing more will come: the producers skip the rest
 		}
-		if (!bm || L.status != 0)
-			T.status[d->caller_index] = L.status; // (block mode: the status words are cleared before the launch)
+		if (!bm)
+			T.status[d->caller_index] = L.status;
+		else if (L.status != 0)
+		{
+			// (block mode: the status words are cleared before the launch -- or, after the team walk, already hold
+			// the reference codes, which a block that was left undecodable must not replace)
+			if (T.keep_status)
+				atomicCAS(reinterpret_cast<int*>(T.status + d->caller_index), 0, L.status);
+			else
+				T.status[d->caller_index] = L.status;
+		}
 	}
 }
 
@@ -523,7 +532,7 @@ __device__ void walk_frame_group(const DevTables& T, uint32_t base, uint32_t lan
 	int status = walk_framing(d->src, d->src_size, d->vertex_size, 0, version);
 	if (status == 0 && d->src_size - 1 != tail_padded(d->vertex_size, version))
 		status = -3; // (:1868-1869)
-	if (status != 0)
+	if (status != 0 && !T.keep_status)
 		T.status[d->caller_index] = status;
 }
 
