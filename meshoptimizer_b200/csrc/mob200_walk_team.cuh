@@ -7,16 +7,17 @@
 //   helper warps   stream the encoded bytes through a shared-memory ring in 512-byte windows and, for EVERY byte
 //                  position p of a window and every field width w in {1, 2, 4} bits, work out how many bytes a group of
 //                  that width starting at p would take (2w + its all-ones fields: SWAR per-byte counts, sliding-window
-//                  sums by doubling) into position-indexed step tables -- ahead of the chain, window after window;
-//   chain warp     follows the stream: control bytes, per bit-packed byte-channel the header, then ONE table byte and one
-//                  add per group (add -> LDS -> add, ~33 cycles), literal and zero channels in O(1); it writes nothing but
-//                  the end offset of every block (the block-offset table, DevTables::block_offset) and the stream's
-//                  reference return code (:1827-1869).
+//                  sums by doubling) -- table T_w -- and how many bytes TWO consecutive groups of that width would
+//                  take, P_w[p] = T_w[p] + T_w[p + T_w[p]], into position-indexed step tables, ahead of the chain,
+//                  window after window;
+//   chain warp     follows the stream: control bytes (turned into bit masks, so that only bit-packed byte-channels cost
+//                  a loop iteration: runs of literal / zero channels are one popcount), per bit-packed channel the
+//                  header, then ONE table byte and one add per group or per PAIR of groups of equal width
+//                  (add -> LDS -> add, ~40 cycles); it writes nothing but the end offset of every block (the
+//                  block-offset table, DevTables::block_offset) and the stream's reference return code (:1827-1869).
 //
 // The decode then runs in block mode (mob200_walker.cuh walk_group<true>): every block is walked again by its own lane
-// -- this time in parallel, group-table rows and all -- and decoded.  Against the fused one-warp-per-stream walker this
-// replaces, the serial part per bit-packed channel drops from ~2400 cycles (tables built on the chain's own warp) to
-// ~700.
+// -- this time in parallel, group-table rows and all -- and decoded.
 #pragma once
 
 #include "mob200_device.cuh"
@@ -26,19 +27,25 @@
 namespace mob200
 {
 
-constexpr uint32_t kTeamHelpers = 2;
+constexpr uint32_t kTeamHelpers = 3;
 constexpr uint32_t kTeamThreads = 32 * (1 + kTeamHelpers);
 constexpr uint32_t kTeamWindow = 512;                          // bytes per window
-constexpr uint32_t kTeamWindows = 8;                           // windows in the ring
-constexpr uint32_t kTeamRing = kTeamWindow * kTeamWindows;     // 4 KB
-constexpr uint32_t kTeamMirror = 512;                          // the first 512 entries again behind the end: a channel (<= 16 + 16 * 24 bytes) never wraps
+constexpr uint32_t kTeamWindows = 4;                           // windows in the ring
+constexpr uint32_t kTeamRing = kTeamWindow * kTeamWindows;     // 2 KB
+constexpr uint32_t kTeamMirror = 512;                          // the first 512 entries again behind the end: a channel (<= 4 + 16 * 24 bytes) never wraps
 constexpr uint32_t kTeamTable = kTeamRing + kTeamMirror;
-// shared memory: data ring (+ mirror), five step tables indexed by ring position (widths {0,1,2,4,8}: 0 and 8 are constant), flags
+constexpr uint32_t kTeamStage = 512 + 32;                      // a helper's private copy of T_w for its window and the 32 positions behind it
+// shared memory: data ring (+ mirror); step tables indexed by ring position -- T for the width indices {0,1,2,4,8 bits}
+// (0 and 8 are constants: 0 and 16 bytes), P for {1,2,4,8 bits} (a pair of zero groups is the T_0 table again); the
+// helpers' staging areas; the flags
 constexpr uint32_t kTeamSmemData = 0;
-constexpr uint32_t kTeamSmemTables = kTeamSmemData + kTeamTable;
-constexpr uint32_t kTeamSmemFlags = kTeamSmemTables + 5 * kTeamTable; // ready[kTeamWindows], consumed
+constexpr uint32_t kTeamSmemT = kTeamSmemData + kTeamTable;
+constexpr uint32_t kTeamSmemP = kTeamSmemT + 5 * kTeamTable; // P tables of width indices 1..4 at (idx - 1)
+constexpr uint32_t kTeamSmemStage = kTeamSmemP + 4 * kTeamTable;
+constexpr uint32_t kTeamSmemFlags = kTeamSmemStage + kTeamHelpers * 3 * kTeamStage; // ready[kTeamWindows], consumed
 constexpr uint32_t kTeamSmemBytes = kTeamSmemFlags + (kTeamWindows + 1) * 4 + 12;
 constexpr uint32_t kTeamStop = 0x7fffffffu; // "consumed" value that tells the helpers the chain is done
+static_assert((kTeamSmemStage & 15) == 0 && (kTeamStage & 15) == 0 && (kTeamSmemFlags & 3) == 0, "alignment");
 
 __device__ __forceinline__ uint32_t lds_acquire_u32(uint32_t a)
 {
@@ -52,10 +59,56 @@ __device__ __forceinline__ void sts_release_u32(uint32_t a, uint32_t v)
 	asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+	return v;
+}
+
+// T_w of the 16 positions that start at `piece` (relative to org): bytes a w-bit group starting there takes
+template <int kWidthIndex>
+__device__ __forceinline__ void team_sizes(const uint32_t w[6], uint32_t out[4])
+{
+	uint32_t n[6];
+#pragma unroll
+	for (int j = 0; j < 6; ++j)
+		n[j] = kWidthIndex == 1 ? bytes_n1(w[j]) : (kWidthIndex == 2 ? bytes_n2(w[j]) : bytes_n4(w[j]));
+	window_sums<(kWidthIndex == 1 ? 2 : (kWidthIndex == 2 ? 4 : 8))>(n, out);
+	const uint32_t fixed = (kWidthIndex == 1 ? 0x02020202u : (kWidthIndex == 2 ? 0x04040404u : 0x08080808u));
+#pragma unroll
+	for (int j = 0; j < 4; ++j)
+		out[j] += fixed;
+}
+
+// 24 bytes from `piece` on (16-byte aligned), never beyond rel_limit
+__device__ __forceinline__ void team_load(const uint8_t* org, uint32_t piece, uint32_t rel_limit, uint32_t w[6])
+{
+#pragma unroll
+	for (int j = 0; j < 6; ++j)
+		w[j] = 0;
+	if (piece < rel_limit)
+	{
+		const uint4 a = __ldg(reinterpret_cast<const uint4*>(org + piece));
+		w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w;
+	}
+	if (piece + 16 < rel_limit)
+	{
+		const uint2 b = __ldg(reinterpret_cast<const uint2*>(org + piece + 16));
+		w[4] = b.x, w[5] = b.y;
+	}
+}
+
 // ---- helper warps: window k of the stream -> data ring + step tables --------------------------------------------------
 __device__ void team_helper(uint32_t helper, uint32_t lane, uint32_t smem, const uint8_t* org, uint32_t rel_limit, uint32_t n_windows)
 {
 	const uint32_t flags = smem + kTeamSmemFlags;
+	const uint32_t stage = smem + kTeamSmemStage + helper * 3 * kTeamStage;
 	for (uint32_t k = helper; k < n_windows; k += kTeamHelpers)
 	{
 		// the slot's previous window (k - kTeamWindows) must not be needed by the chain any more
@@ -68,57 +121,62 @@ __device__ void team_helper(uint32_t helper, uint32_t lane, uint32_t smem, const
 		if (consumed == kTeamStop)
 			break; // the chain has finished (or given up on) the stream
 
-		// 24 bytes from the lane's 16-byte piece on (the sliding windows look up to 7 bytes past a position, and the last
-		// lane's run into the next window: its bytes are read straight from global memory, never beyond rel_limit)
 		const uint32_t piece = k * kTeamWindow + lane * 16;
-		uint32_t w[6] = {0, 0, 0, 0, 0, 0};
-		if (piece < rel_limit)
-		{
-			const uint4 a = __ldg(reinterpret_cast<const uint4*>(org + piece));
-			w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w;
-		}
-		if (piece + 16 < rel_limit)
-		{
-			const uint2 b = __ldg(reinterpret_cast<const uint2*>(org + piece + 16));
-			w[4] = b.x, w[5] = b.y;
-		}
-		const uint32_t pos = (k % kTeamWindows) * kTeamWindow + lane * 16;
+		const uint32_t slot = (k % kTeamWindows) * kTeamWindow + lane * 16;
 		const bool mirror = (k % kTeamWindows) == 0; // the first window of the ring is kept twice
-		asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem + kTeamSmemData + pos), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+		uint32_t w[6], t1[4], t2[4], t4[4];
+		team_load(org, piece, rel_limit, w);
+		sts_v4(smem + kTeamSmemData + slot, w[0], w[1], w[2], w[3]);
 		if (mirror)
-			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem + kTeamSmemData + kTeamRing + pos), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+			sts_v4(smem + kTeamSmemData + kTeamRing + slot, w[0], w[1], w[2], w[3]);
+		team_sizes<1>(w, t1);
+		team_sizes<2>(w, t2);
+		team_sizes<3>(w, t4);
+		sts_v4(stage + 0 * kTeamStage + lane * 16, t1[0], t1[1], t1[2], t1[3]);
+		sts_v4(stage + 1 * kTeamStage + lane * 16, t2[0], t2[1], t2[2], t2[3]);
+		sts_v4(stage + 2 * kTeamStage + lane * 16, t4[0], t4[1], t4[2], t4[3]);
+		// the 32 positions behind the window (a second group of a pair may start there): lanes 0 and 1 again
+		if (lane < 2)
+		{
+			uint32_t wx[6], x1[4], x2[4], x4[4];
+			team_load(org, (k + 1) * kTeamWindow + lane * 16, rel_limit, wx);
+			team_sizes<1>(wx, x1);
+			team_sizes<2>(wx, x2);
+			team_sizes<3>(wx, x4);
+			sts_v4(stage + 0 * kTeamStage + 512 + lane * 16, x1[0], x1[1], x1[2], x1[3]);
+			sts_v4(stage + 1 * kTeamStage + 512 + lane * 16, x2[0], x2[1], x2[2], x2[3]);
+			sts_v4(stage + 2 * kTeamStage + 512 + lane * 16, x4[0], x4[1], x4[2], x4[3]);
+		}
+		__syncwarp();
 
-		uint32_t n[6], out[4];
-		// width index 1: 1-bit fields, windows of 2 bytes; 2: 2-bit, 4 bytes; 3: 4-bit, 8 bytes.  Entry = bytes the group takes.
+		// pairs: P_w[p] = T_w[p] + T_w[p + T_w[p]] (T <= 24: the second group starts inside the staged range)
 #pragma unroll
-		for (int j = 0; j < 6; ++j)
-			n[j] = bytes_n1(w[j]);
-		window_sums<2>(n, out);
+		for (int wi = 0; wi < 3; ++wi)
 		{
-			const uint32_t t = smem + kTeamSmemTables + 1 * kTeamTable + pos;
-			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(out[0] + 0x02020202u), "r"(out[1] + 0x02020202u), "r"(out[2] + 0x02020202u), "r"(out[3] + 0x02020202u) : "memory");
-			if (mirror)
-				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(t + kTeamRing), "r"(out[0] + 0x02020202u), "r"(out[1] + 0x02020202u), "r"(out[2] + 0x02020202u), "r"(out[3] + 0x02020202u) : "memory");
-		}
+			const uint32_t* t = wi == 0 ? t1 : (wi == 1 ? t2 : t4);
+			const uint32_t sbase = stage + wi * kTeamStage + lane * 16;
+			uint32_t p[4];
 #pragma unroll
-		for (int j = 0; j < 6; ++j)
-			n[j] = bytes_n2(w[j]);
-		window_sums<4>(n, out);
-		{
-			const uint32_t t = smem + kTeamSmemTables + 2 * kTeamTable + pos;
-			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(out[0] + 0x04040404u), "r"(out[1] + 0x04040404u), "r"(out[2] + 0x04040404u), "r"(out[3] + 0x04040404u) : "memory");
-			if (mirror)
-				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(t + kTeamRing), "r"(out[0] + 0x04040404u), "r"(out[1] + 0x04040404u), "r"(out[2] + 0x04040404u), "r"(out[3] + 0x04040404u) : "memory");
-		}
+			for (int j = 0; j < 4; ++j)
+			{
+				uint32_t acc = 0;
 #pragma unroll
-		for (int j = 0; j < 6; ++j)
-			n[j] = bytes_n4(w[j]);
-		window_sums<8>(n, out);
-		{
-			const uint32_t t = smem + kTeamSmemTables + 3 * kTeamTable + pos;
-			asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(t), "r"(out[0] + 0x08080808u), "r"(out[1] + 0x08080808u), "r"(out[2] + 0x08080808u), "r"(out[3] + 0x08080808u) : "memory");
+				for (int b = 0; b < 4; ++b)
+				{
+					const uint32_t first = (t[j] >> (8 * b)) & 0xffu;
+					acc |= (first + lds_u8(sbase + 4 * j + b + first)) << (8 * b);
+				}
+				p[j] = acc;
+			}
+			const uint32_t tt = smem + kTeamSmemT + (wi + 1) * kTeamTable + slot;
+			const uint32_t pt = smem + kTeamSmemP + wi * kTeamTable + slot;
+			sts_v4(tt, t[0], t[1], t[2], t[3]);
+			sts_v4(pt, p[0], p[1], p[2], p[3]);
 			if (mirror)
-				asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(t + kTeamRing), "r"(out[0] + 0x08080808u), "r"(out[1] + 0x08080808u), "r"(out[2] + 0x08080808u), "r"(out[3] + 0x08080808u) : "memory");
+			{
+				sts_v4(tt + kTeamRing, t[0], t[1], t[2], t[3]);
+				sts_v4(pt + kTeamRing, p[0], p[1], p[2], p[3]);
+			}
 		}
 		__syncwarp();
 		if (lane == 0)
@@ -160,6 +218,51 @@ __device__ __forceinline__ void team_need(uint32_t smem, uint32_t rel, uint32_t 
 	}
 }
 
+// even bits of x (bit 2i -> bit i)
+__device__ __forceinline__ uint32_t even_bits(uint32_t x)
+{
+	x &= 0x55555555u;
+	x = (x | (x >> 1)) & 0x33333333u;
+	x = (x | (x >> 2)) & 0x0f0f0f0fu;
+	x = (x | (x >> 4)) & 0x00ff00ffu;
+	return (x | (x >> 8)) & 0xffffu;
+}
+
+// One bit-packed byte-channel: header at rel, then `groups` groups.  Returns false if the channel is malformed.
+__device__ __forceinline__ bool team_channel(uint32_t smem, uint32_t& rel, uint32_t rel_end, uint32_t groups, uint32_t hdr, uint32_t version, uint32_t ctrl,
+    uint32_t n_windows, uint32_t& have_until, uint32_t& released, uint32_t lane)
+{
+	if (rel_end - rel < hdr) // (:1376)
+		return false;
+	team_need(smem, rel, hdr + 16 * kGroupReadLimit + 8, n_windows, have_until, released, lane);
+	uint32_t sel_bits = team_u32(smem, rel);
+	rel += hdr;
+
+	// The chain: one table byte per group, or per pair of neighbouring groups with the same selector (never the last two: the
+	// position of the LAST group is needed for the reference's 24-byte rule, :1385,:1415, which is tested once, there).
+	// Tables are indexed by ring position; a channel never wraps thanks to the mirrored head of the ring.
+	const uint32_t tbase = smem + kTeamSmemT, pbase = smem + kTeamSmemP - kTeamTable; // (P tables start at width index 1)
+	const uint32_t p0 = rel & (kTeamRing - 1);
+	uint32_t p = p0, p_last = p0;
+	const uint32_t shift = version ? ctrl : 0u;
+	for (uint32_t g = 0; g < groups;)
+	{
+		const uint32_t sel = sel_bits & 3u, nsel = (sel_bits >> 2) & 3u;
+		const uint32_t idx = version ? sel + shift : (sel ? sel + 1u : 0u);
+		const bool pair = g + 2 < groups && sel == nsel && idx != 0;
+		uint32_t slot_base = (pair ? pbase : tbase) + idx * kTeamTable;
+		asm volatile("" : "+r"(slot_base)); // (keeps the table base out of the sum with the running position)
+		const uint32_t step = lds_u8(slot_base + p);
+		p_last = p;
+		sel_bits >>= pair ? 4 : 2;
+		g += pair ? 2 : 1;
+		p += step;
+	}
+	const uint32_t rel_last = rel + (p_last - p0);
+	rel += p - p0;
+	return !(rel_last > rel_end || rel_end - rel_last < kGroupReadLimit);
+}
+
 __device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32_t smem, int framing_status, uint32_t version, uint32_t n_windows)
 {
 	const DevStream* d = T.streams + s;
@@ -178,7 +281,6 @@ __device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32
 	uint32_t done = 0;
 	const bool framed = status == 0;
 	uint32_t have_until = 0, released = 0;
-	const uint32_t tab = smem + kTeamSmemTables;
 
 	if (framed && nblocks)
 	{
@@ -192,77 +294,61 @@ __device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32
 			const uint32_t hdr = (groups + 3) / 4;
 			const uint32_t ctrl_bytes = version ? vs / 4 : 0;
 			bool bad = rel_end - rel < ctrl_bytes;
-
-			// control bytes of the first 64 byte-channels are kept in registers; wider vertices read the rest from global memory
 			const uint8_t* control = src + (rel - rel0);
-			uint32_t cw0 = 0, cw1 = 0, cw2 = 0, cw3 = 0;
-			if (!bad && version)
+
+			// byte-channels in chunks of 32: their control values (2 bits each; v0: all bit-packed) become two bit masks
+			for (uint32_t k0 = 0; k0 < vs && !bad; k0 += 32)
 			{
-				team_need(smem, rel, 20, n_windows, have_until, released, lane);
-				cw0 = team_u32(smem, rel), cw1 = team_u32(smem, rel + 4), cw2 = team_u32(smem, rel + 8), cw3 = team_u32(smem, rel + 12);
-			}
-			if (!bad)
-				rel += ctrl_bytes;
-
-			for (uint32_t k = 0; k < vs && !bad; ++k)
-			{
-				uint32_t cbyte;
-				if (k < 64)
+				const uint32_t kn = min(32u, vs - k0);
+				const uint32_t live = kn == 32 ? 0xffffffffu : ((1u << kn) - 1u);
+				uint32_t c_lo = 0, c_hi = 0; // control bits of channels k0 .. k0 + 15 / k0 + 16 .. k0 + 31
+				if (version)
 				{
-					const uint32_t wsel = k >> 4;
-					const uint32_t word = wsel == 0 ? cw0 : (wsel == 1 ? cw1 : (wsel == 2 ? cw2 : cw3));
-					cbyte = (word >> (((k >> 2) & 3u) * 8)) & 0xffu;
+					if (k0 == 0)
+					{
+						team_need(smem, rel, 12, n_windows, have_until, released, lane);
+						c_lo = team_u32(smem, rel), c_hi = team_u32(smem, rel + 4);
+						rel += ctrl_bytes;
+					}
+					else
+					{
+						// (vertices wider than 32 bytes: the rest of the control bytes comes from global memory -- the ring has moved on)
+						for (uint32_t j = 0; j < 4 && k0 / 4 + j < ctrl_bytes; ++j)
+							c_lo |= (uint32_t)__ldg(control + k0 / 4 + j) << (8 * j);
+						for (uint32_t j = 0; j < 4 && k0 / 4 + 4 + j < ctrl_bytes; ++j)
+							c_hi |= (uint32_t)__ldg(control + k0 / 4 + 4 + j) << (8 * j);
+					}
 				}
-				else
-					cbyte = version ? __ldg(control + (k >> 2)) : 0u;
-				const uint32_t ctrl = (cbyte >> ((k & 3) * 2)) & 3u;
-
-				if (ctrl == 3)
+				const uint32_t bit0 = even_bits(c_lo) | (even_bits(c_hi) << 16), bit1 = even_bits(c_lo >> 1) | (even_bits(c_hi >> 1) << 16);
+				uint32_t packed = ~bit1 & live;            // control 0 / 1
+				const uint32_t literal = bit1 & bit0 & live; // control 3 (n raw bytes); control 2 stores nothing
+				uint32_t below_done = 0;                   // channels of the chunk already accounted for
+				while (!bad)
 				{
-					if (rel_end - rel < na) // literal bytes (:1546-1554): the 16-aligned count must be readable
+					const uint32_t k = packed ? (uint32_t)__ffs((int)packed) - 1u : 32u;
+					const uint32_t upto = k >= 32 ? 0xffffffffu : ((1u << k) - 1u);
+					// the literal channels in front of channel k (:1546-1554: the 16-aligned count must be readable for each;
+					// positions only grow, so the last one of the run decides)
+					const uint32_t lits = (uint32_t)__popc(literal & upto & ~below_done);
+					if (lits)
+					{
+						if (rel_end - rel < (lits - 1) * n || rel_end - rel - (lits - 1) * n < na)
+						{
+							bad = true;
+							break;
+						}
+						rel += lits * n;
+					}
+					if (k >= 32)
+						break;
+					const uint32_t ctrl = (((k < 16 ? c_lo : c_hi) >> ((k & 15u) * 2u)) & 3u);
+					if (!team_channel(smem, rel, rel_end, groups, hdr, version, ctrl, n_windows, have_until, released, lane))
 					{
 						bad = true;
 						break;
 					}
-					rel += n;
-				}
-				else if (ctrl != 2)
-				{
-					if (rel_end - rel < hdr) // (:1376)
-					{
-						bad = true;
-						break;
-					}
-					team_need(smem, rel, hdr + 16 * kGroupReadLimit + 8, n_windows, have_until, released, lane);
-					uint32_t sel_bits = team_u32(smem, rel);
-					rel += hdr;
-
-					// the chain: one table byte per group (tables indexed by ring position; a channel never wraps thanks to the
-					// mirrored head of the ring).  The 24-byte rule (:1385,:1415) is tested once, on the last group's position.
-					uint32_t p = rel & (kTeamRing - 1);
-					const uint32_t p0 = p;
-					uint32_t p_last = p;
-					uint32_t idx = (sel_bits & 3u) + (version ? ctrl : (uint32_t)((sel_bits & 3u) != 0u));
-					uint32_t slot_base = tab + idx * kTeamTable;
-#pragma unroll 4
-					for (uint32_t g = 0; g < groups; ++g)
-					{
-						uint32_t step;
-						asm volatile("ld.shared.u8 %0, [%1];" : "=r"(step) : "r"(slot_base + p));
-						p_last = p;
-						sel_bits >>= 2;
-						idx = (sel_bits & 3u) + (version ? ctrl : (uint32_t)((sel_bits & 3u) != 0u));
-						slot_base = tab + idx * kTeamTable;
-						asm volatile("" : "+r"(slot_base)); // (keeps the table base out of the sum with the running position)
-						p += step;
-					}
-					const uint32_t rel_last = rel + (p_last - p0);
-					rel += p - p0;
-					if (rel_last > rel_end || rel_end - rel_last < kGroupReadLimit)
-					{
-						bad = true;
-						break;
-					}
+					packed &= packed - 1u;
+					below_done = upto | (1u << k);
 				}
 			}
 
@@ -301,11 +387,12 @@ __global__ void __launch_bounds__(kTeamThreads) walk_team_kernel(DevTables T)
 
 	for (uint32_t s = blockIdx.x; s < T.n_streams; s += gridDim.x)
 	{
-		// constant step tables (a zero group takes no bytes, an 8-bit group 16) and the flags
+		// constant step tables (a zero group takes no bytes, an 8-bit group 16, a pair of them 32) and the flags
 		for (uint32_t i = threadIdx.x * 16; i < kTeamTable; i += kTeamThreads * 16)
 		{
-			asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem + kTeamSmemTables + i), "r"(0u) : "memory");
-			asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem + kTeamSmemTables + 4 * kTeamTable + i), "r"(0x10101010u) : "memory");
+			sts_v4(smem + kTeamSmemT + i, 0u, 0u, 0u, 0u);
+			sts_v4(smem + kTeamSmemT + 4 * kTeamTable + i, 0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u);
+			sts_v4(smem + kTeamSmemP + 3 * kTeamTable + i, 0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
 		}
 		if (threadIdx.x <= kTeamWindows)
 			reinterpret_cast<volatile uint32_t*>(team_smem + kTeamSmemFlags)[threadIdx.x] = 0;
