@@ -238,25 +238,39 @@ __device__ __forceinline__ bool team_channel(uint32_t smem, uint32_t& rel, uint3
 	uint32_t sel_bits = team_u32(smem, rel);
 	rel += hdr;
 
-	// The chain: one table byte per group, or per pair of neighbouring groups with the same selector (never the last two: the
-	// position of the LAST group is needed for the reference's 24-byte rule, :1385,:1415, which is tested once, there).
+	// The chain: one table byte per group, or per PAIR of groups (2j, 2j+1) with the same selector -- never the last group,
+	// whose position is needed for the reference's 24-byte rule (:1385,:1415), tested once, there.  Which table a step
+	// reads depends on the header only: lane j works out the (at most two) steps of pair slot j, the eight descriptors
+	// are broadcast up front, and the dependent chain itself is nothing but  LDS -> add -> add  per step.
 	// Tables are indexed by ring position; a channel never wraps thanks to the mirrored head of the ring.
-	const uint32_t tbase = smem + kTeamSmemT, pbase = smem + kTeamSmemP - kTeamTable; // (P tables start at width index 1)
+	uint32_t mine = 0; // table base of step A | table base of step B << 16 (offsets from `smem`; 0 = no such step)
+	{
+		const uint32_t j = lane & 7u, g0 = 2 * j, g1 = g0 + 1;
+		const uint32_t s0 = (sel_bits >> (4 * j)) & 3u, s1 = (sel_bits >> (4 * j + 2)) & 3u;
+		const uint32_t shift = version ? ctrl : 0u;
+		const uint32_t i0 = version ? s0 + shift : (s0 ? s0 + 1u : 0u), i1 = version ? s1 + shift : (s1 ? s1 + 1u : 0u);
+		const bool pair = g1 + 1 < groups && s0 == s1 && i0 != 0; // (g1 is not the last group)
+		const uint32_t a = g0 < groups ? (pair ? kTeamSmemP - kTeamTable : kTeamSmemT) + i0 * kTeamTable : 0u;
+		const uint32_t b = (g1 < groups && !pair) ? kTeamSmemT + i1 * kTeamTable : 0u;
+		mine = a | (b << 16);
+	}
 	const uint32_t p0 = rel & (kTeamRing - 1);
 	uint32_t p = p0, p_last = p0;
-	const uint32_t shift = version ? ctrl : 0u;
-	for (uint32_t g = 0; g < groups;)
+#pragma unroll
+	for (uint32_t j = 0; j < 8; ++j)
 	{
-		const uint32_t sel = sel_bits & 3u, nsel = (sel_bits >> 2) & 3u;
-		const uint32_t idx = version ? sel + shift : (sel ? sel + 1u : 0u);
-		const bool pair = g + 2 < groups && sel == nsel && idx != 0;
-		uint32_t slot_base = (pair ? pbase : tbase) + idx * kTeamTable;
-		asm volatile("" : "+r"(slot_base)); // (keeps the table base out of the sum with the running position)
-		const uint32_t step = lds_u8(slot_base + p);
-		p_last = p;
-		sel_bits >>= pair ? 4 : 2;
-		g += pair ? 2 : 1;
-		p += step;
+		const uint32_t dsc = __shfl_sync(0xffffffffu, mine, j);
+		const uint32_t a = dsc & 0xffffu, b = dsc >> 16;
+		if (a)
+		{
+			p_last = p;
+			p += lds_u8(smem + a + p);
+		}
+		if (b)
+		{
+			p_last = p;
+			p += lds_u8(smem + b + p);
+		}
 	}
 	const uint32_t rel_last = rel + (p_last - p0);
 	rel += p - p0;
