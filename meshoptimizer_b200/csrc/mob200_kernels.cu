@@ -319,7 +319,7 @@ cudaError_t launch_walk_team(const DevTables& T, int sm_count, cudaStream_t stre
 	if (T.n_streams == 0)
 		return cudaSuccess;
 	// one CTA per stream, at most what the device holds at once (the rest by grid stride)
-	const uint32_t cap = (uint32_t)sm_count * 7u;
+	const uint32_t cap = (uint32_t)sm_count * 10u;
 	const uint32_t grid = T.n_streams < cap ? T.n_streams : cap;
 	walk_team_kernel<<<grid, kTeamThreads, kTeamSmemBytes, stream>>>(T);
 	return cudaGetLastError();

@@ -7,14 +7,18 @@
 //   helper warps   stream the encoded bytes through a shared-memory ring in 512-byte windows and, for EVERY byte
 //                  position p of a window and every field width w in {1, 2, 4} bits, work out how many bytes a group of
 //                  that width starting at p would take (2w + its all-ones fields: SWAR per-byte counts, sliding-window
-//                  sums by doubling) -- table T_w -- and how many bytes TWO consecutive groups of that width would
-//                  take, P_w[p] = T_w[p] + T_w[p + T_w[p]], into position-indexed step tables, ahead of the chain,
-//                  window after window;
+//                  sums by doubling) into position-indexed step tables T_w, ahead of the chain, window after window;
 //   chain warp     follows the stream: control bytes (turned into bit masks, so that only bit-packed byte-channels cost
 //                  a loop iteration: runs of literal / zero channels are one popcount), per bit-packed channel the
-//                  header, then ONE table byte and one add per group or per PAIR of groups of equal width
-//                  (add -> LDS -> add, ~40 cycles); it writes nothing but the end offset of every block (the
-//                  block-offset table, DevTables::block_offset) and the stream's reference return code (:1827-1869).
+//                  header, then ONE table byte and one add per group (add -> LDS -> add, ~40 cycles; which table a step
+//                  reads is worked out from the header by the lanes in parallel, off the chain); it writes nothing but the
+//                  end offset of every block (the block-offset table, DevTables::block_offset) and the stream's reference
+//                  return code (:1827-1869).
+//
+// Measured (r2, B200): one monolithic stream 0.63 -> 1.2 GB/s, 1024 x 65536-vertex streams 7.95 -> 4.4 ms against the
+// fused one-warp-per-stream walker.  What is left is the latency of a lone warp's instruction stream (~6 cycles per
+// instruction, ~2500 per block), not the table look-ups: step tables for PAIRS of equal-width groups (half the chain
+// steps, 2.5x the helpers' work) measured 5-15 % slower and were dropped.
 //
 // The decode then runs in block mode (mob200_walker.cuh walk_group<true>): every block is walked again by its own lane
 // -- this time in parallel, group-table rows and all -- and decoded.
@@ -27,25 +31,21 @@
 namespace mob200
 {
 
-constexpr uint32_t kTeamHelpers = 3;
+constexpr uint32_t kTeamHelpers = 2;
 constexpr uint32_t kTeamThreads = 32 * (1 + kTeamHelpers);
 constexpr uint32_t kTeamWindow = 512;                          // bytes per window
 constexpr uint32_t kTeamWindows = 4;                           // windows in the ring
 constexpr uint32_t kTeamRing = kTeamWindow * kTeamWindows;     // 2 KB
 constexpr uint32_t kTeamMirror = 512;                          // the first 512 entries again behind the end: a channel (<= 4 + 16 * 24 bytes) never wraps
 constexpr uint32_t kTeamTable = kTeamRing + kTeamMirror;
-constexpr uint32_t kTeamStage = 512 + 32;                      // a helper's private copy of T_w for its window and the 32 positions behind it
-// shared memory: data ring (+ mirror); step tables indexed by ring position -- T for the width indices {0,1,2,4,8 bits}
-// (0 and 8 are constants: 0 and 16 bytes), P for {1,2,4,8 bits} (a pair of zero groups is the T_0 table again); the
-// helpers' staging areas; the flags
+// shared memory: data ring (+ mirror); five step tables indexed by ring position, one per width index {0,1,2,4,8 bits}
+// (0 and 8 are constants: 0 and 16 bytes); the flags
 constexpr uint32_t kTeamSmemData = 0;
 constexpr uint32_t kTeamSmemT = kTeamSmemData + kTeamTable;
-constexpr uint32_t kTeamSmemP = kTeamSmemT + 5 * kTeamTable; // P tables of width indices 1..4 at (idx - 1)
-constexpr uint32_t kTeamSmemStage = kTeamSmemP + 4 * kTeamTable;
-constexpr uint32_t kTeamSmemFlags = kTeamSmemStage + kTeamHelpers * 3 * kTeamStage; // ready[kTeamWindows], consumed
+constexpr uint32_t kTeamSmemFlags = kTeamSmemT + 5 * kTeamTable; // ready[kTeamWindows], consumed
 constexpr uint32_t kTeamSmemBytes = kTeamSmemFlags + (kTeamWindows + 1) * 4 + 12;
 constexpr uint32_t kTeamStop = 0x7fffffffu; // "consumed" value that tells the helpers the chain is done
-static_assert((kTeamSmemStage & 15) == 0 && (kTeamStage & 15) == 0 && (kTeamSmemFlags & 3) == 0, "alignment");
+static_assert((kTeamSmemFlags & 3) == 0, "alignment");
 
 __device__ __forceinline__ uint32_t lds_acquire_u32(uint32_t a)
 {
@@ -108,7 +108,6 @@ __device__ __forceinline__ void team_load(const uint8_t* org, uint32_t piece, ui
 __device__ void team_helper(uint32_t helper, uint32_t lane, uint32_t smem, const uint8_t* org, uint32_t rel_limit, uint32_t n_windows)
 {
 	const uint32_t flags = smem + kTeamSmemFlags;
-	const uint32_t stage = smem + kTeamSmemStage + helper * 3 * kTeamStage;
 	for (uint32_t k = helper; k < n_windows; k += kTeamHelpers)
 	{
 		// the slot's previous window (k - kTeamWindows) must not be needed by the chain any more
@@ -124,60 +123,23 @@ __device__ void team_helper(uint32_t helper, uint32_t lane, uint32_t smem, const
 		const uint32_t piece = k * kTeamWindow + lane * 16;
 		const uint32_t slot = (k % kTeamWindows) * kTeamWindow + lane * 16;
 		const bool mirror = (k % kTeamWindows) == 0; // the first window of the ring is kept twice
-		uint32_t w[6], t1[4], t2[4], t4[4];
+		uint32_t w[6], t[4];
 		team_load(org, piece, rel_limit, w);
 		sts_v4(smem + kTeamSmemData + slot, w[0], w[1], w[2], w[3]);
 		if (mirror)
 			sts_v4(smem + kTeamSmemData + kTeamRing + slot, w[0], w[1], w[2], w[3]);
-		team_sizes<1>(w, t1);
-		team_sizes<2>(w, t2);
-		team_sizes<3>(w, t4);
-		sts_v4(stage + 0 * kTeamStage + lane * 16, t1[0], t1[1], t1[2], t1[3]);
-		sts_v4(stage + 1 * kTeamStage + lane * 16, t2[0], t2[1], t2[2], t2[3]);
-		sts_v4(stage + 2 * kTeamStage + lane * 16, t4[0], t4[1], t4[2], t4[3]);
-		// the 32 positions behind the window (a second group of a pair may start there): lanes 0 and 1 again
-		if (lane < 2)
-		{
-			uint32_t wx[6], x1[4], x2[4], x4[4];
-			team_load(org, (k + 1) * kTeamWindow + lane * 16, rel_limit, wx);
-			team_sizes<1>(wx, x1);
-			team_sizes<2>(wx, x2);
-			team_sizes<3>(wx, x4);
-			sts_v4(stage + 0 * kTeamStage + 512 + lane * 16, x1[0], x1[1], x1[2], x1[3]);
-			sts_v4(stage + 1 * kTeamStage + 512 + lane * 16, x2[0], x2[1], x2[2], x2[3]);
-			sts_v4(stage + 2 * kTeamStage + 512 + lane * 16, x4[0], x4[1], x4[2], x4[3]);
-		}
-		__syncwarp();
-
-		// pairs: P_w[p] = T_w[p] + T_w[p + T_w[p]] (T <= 24: the second group starts inside the staged range)
-#pragma unroll
-		for (int wi = 0; wi < 3; ++wi)
-		{
-			const uint32_t* t = wi == 0 ? t1 : (wi == 1 ? t2 : t4);
-			const uint32_t sbase = stage + wi * kTeamStage + lane * 16;
-			uint32_t p[4];
-#pragma unroll
-			for (int j = 0; j < 4; ++j)
-			{
-				uint32_t acc = 0;
-#pragma unroll
-				for (int b = 0; b < 4; ++b)
-				{
-					const uint32_t first = (t[j] >> (8 * b)) & 0xffu;
-					acc |= (first + lds_u8(sbase + 4 * j + b + first)) << (8 * b);
-				}
-				p[j] = acc;
-			}
-			const uint32_t tt = smem + kTeamSmemT + (wi + 1) * kTeamTable + slot;
-			const uint32_t pt = smem + kTeamSmemP + wi * kTeamTable + slot;
-			sts_v4(tt, t[0], t[1], t[2], t[3]);
-			sts_v4(pt, p[0], p[1], p[2], p[3]);
-			if (mirror)
-			{
-				sts_v4(tt + kTeamRing, t[0], t[1], t[2], t[3]);
-				sts_v4(pt + kTeamRing, p[0], p[1], p[2], p[3]);
-			}
-		}
+		team_sizes<1>(w, t);
+		sts_v4(smem + kTeamSmemT + 1 * kTeamTable + slot, t[0], t[1], t[2], t[3]);
+		if (mirror)
+			sts_v4(smem + kTeamSmemT + 1 * kTeamTable + kTeamRing + slot, t[0], t[1], t[2], t[3]);
+		team_sizes<2>(w, t);
+		sts_v4(smem + kTeamSmemT + 2 * kTeamTable + slot, t[0], t[1], t[2], t[3]);
+		if (mirror)
+			sts_v4(smem + kTeamSmemT + 2 * kTeamTable + kTeamRing + slot, t[0], t[1], t[2], t[3]);
+		team_sizes<3>(w, t);
+		sts_v4(smem + kTeamSmemT + 3 * kTeamTable + slot, t[0], t[1], t[2], t[3]);
+		if (mirror)
+			sts_v4(smem + kTeamSmemT + 3 * kTeamTable + kTeamRing + slot, t[0], t[1], t[2], t[3]);
 		__syncwarp();
 		if (lane == 0)
 			sts_release_u32(flags + (k % kTeamWindows) * 4, k + 1);
@@ -238,38 +200,27 @@ __device__ __forceinline__ bool team_channel(uint32_t smem, uint32_t& rel, uint3
 	uint32_t sel_bits = team_u32(smem, rel);
 	rel += hdr;
 
-	// The chain: one table byte per group, or per PAIR of groups (2j, 2j+1) with the same selector -- never the last group,
-	// whose position is needed for the reference's 24-byte rule (:1385,:1415), tested once, there.  Which table a step
-	// reads depends on the header only: lane j works out the (at most two) steps of pair slot j, the eight descriptors
-	// are broadcast up front, and the dependent chain itself is nothing but  LDS -> add -> add  per step.
+	// The chain: one table byte per group.  Which table a step reads depends on the header only: lane g works out the table of
+	// group g, the descriptors are broadcast up front, and the dependent chain itself is nothing but  LDS -> add -> add  per
+	// step.  The reference's 24-byte rule (:1385,:1415) is tested once, on the position of the last group (positions only grow).
 	// Tables are indexed by ring position; a channel never wraps thanks to the mirrored head of the ring.
-	uint32_t mine = 0; // table base of step A | table base of step B << 16 (offsets from `smem`; 0 = no such step)
+	uint32_t mine = 0; // table of group `lane` (offset from `smem`); 0 = no such group
 	{
-		const uint32_t j = lane & 7u, g0 = 2 * j, g1 = g0 + 1;
-		const uint32_t s0 = (sel_bits >> (4 * j)) & 3u, s1 = (sel_bits >> (4 * j + 2)) & 3u;
-		const uint32_t shift = version ? ctrl : 0u;
-		const uint32_t i0 = version ? s0 + shift : (s0 ? s0 + 1u : 0u), i1 = version ? s1 + shift : (s1 ? s1 + 1u : 0u);
-		const bool pair = g1 + 1 < groups && s0 == s1 && i0 != 0; // (g1 is not the last group)
-		const uint32_t a = g0 < groups ? (pair ? kTeamSmemP - kTeamTable : kTeamSmemT) + i0 * kTeamTable : 0u;
-		const uint32_t b = (g1 < groups && !pair) ? kTeamSmemT + i1 * kTeamTable : 0u;
-		mine = a | (b << 16);
+		const uint32_t g = lane & 15u;
+		const uint32_t sel = (sel_bits >> (2 * g)) & 3u;
+		const uint32_t idx = version ? sel + ctrl : (sel ? sel + 1u : 0u);
+		mine = g < groups ? kTeamSmemT + idx * kTeamTable : 0u;
 	}
 	const uint32_t p0 = rel & (kTeamRing - 1);
 	uint32_t p = p0, p_last = p0;
 #pragma unroll
-	for (uint32_t j = 0; j < 8; ++j)
+	for (uint32_t g = 0; g < 16; ++g)
 	{
-		const uint32_t dsc = __shfl_sync(0xffffffffu, mine, j);
-		const uint32_t a = dsc & 0xffffu, b = dsc >> 16;
+		const uint32_t a = __shfl_sync(0xffffffffu, mine, g);
 		if (a)
 		{
 			p_last = p;
 			p += lds_u8(smem + a + p);
-		}
-		if (b)
-		{
-			p_last = p;
-			p += lds_u8(smem + b + p);
 		}
 	}
 	const uint32_t rel_last = rel + (p_last - p0);
@@ -401,12 +352,11 @@ __global__ void __launch_bounds__(kTeamThreads) walk_team_kernel(DevTables T)
 
 	for (uint32_t s = blockIdx.x; s < T.n_streams; s += gridDim.x)
 	{
-		// constant step tables (a zero group takes no bytes, an 8-bit group 16, a pair of them 32) and the flags
+		// constant step tables (a zero group takes no bytes, an 8-bit group 16) and the flags
 		for (uint32_t i = threadIdx.x * 16; i < kTeamTable; i += kTeamThreads * 16)
 		{
 			sts_v4(smem + kTeamSmemT + i, 0u, 0u, 0u, 0u);
 			sts_v4(smem + kTeamSmemT + 4 * kTeamTable + i, 0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u);
-			sts_v4(smem + kTeamSmemP + 3 * kTeamTable + i, 0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
 		}
 		if (threadIdx.x <= kTeamWindows)
 			reinterpret_cast<volatile uint32_t*>(team_smem + kTeamSmemFlags)[threadIdx.x] = 0;
