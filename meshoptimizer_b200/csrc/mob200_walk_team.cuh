@@ -42,22 +42,10 @@ constexpr uint32_t kTeamTable = kTeamRing + kTeamMirror;
 // (0 and 8 are constants: 0 and 16 bytes); the flags
 constexpr uint32_t kTeamSmemData = 0;
 constexpr uint32_t kTeamSmemT = kTeamSmemData + kTeamTable;
-constexpr uint32_t kTeamSmemFlags = kTeamSmemT + 5 * kTeamTable; // ready[kTeamWindows], consumed
-constexpr uint32_t kTeamSmemBytes = kTeamSmemFlags + (kTeamWindows + 1) * 4 + 12;
-constexpr uint32_t kTeamStop = 0x7fffffffu; // "consumed" value that tells the helpers the chain is done
-static_assert((kTeamSmemFlags & 3) == 0, "alignment");
-
-__device__ __forceinline__ uint32_t lds_acquire_u32(uint32_t a)
-{
-	uint32_t v;
-	asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-	return v;
-}
-
-__device__ __forceinline__ void sts_release_u32(uint32_t a, uint32_t v)
-{
-	asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
+constexpr uint32_t kTeamSmemBars = kTeamSmemT + 5 * kTeamTable; // mbarriers full[kTeamWindows] (helper -> chain), empty[kTeamWindows] (chain -> helpers)
+constexpr uint32_t kTeamSmemStop = kTeamSmemBars + 2 * kTeamWindows * 8; // set by the chain when it is done with the stream
+constexpr uint32_t kTeamSmemBytes = kTeamSmemStop + 16;
+static_assert((kTeamSmemBars & 7) == 0, "alignment");
 
 __device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
 {
@@ -105,20 +93,25 @@ __device__ __forceinline__ void team_load(const uint8_t* org, uint32_t piece, ui
 }
 
 // ---- helper warps: window k of the stream -> data ring + step tables --------------------------------------------------
-__device__ void team_helper(uint32_t helper, uint32_t lane, uint32_t smem, const uint8_t* org, uint32_t rel_limit, uint32_t n_windows)
+__device__ void team_helper(uint32_t helper, uint32_t lane, uint8_t* base, const uint8_t* org, uint32_t rel_limit, uint32_t n_windows)
 {
-	const uint32_t flags = smem + kTeamSmemFlags;
+	const uint32_t smem = smem_addr(base);
+	uint64_t* full = reinterpret_cast<uint64_t*>(base + kTeamSmemBars);
+	uint64_t* empty = full + kTeamWindows;
+	uint32_t* stop = reinterpret_cast<uint32_t*>(base + kTeamSmemStop);
 	for (uint32_t k = helper; k < n_windows; k += kTeamHelpers)
 	{
-		// the slot's previous window (k - kTeamWindows) must not be needed by the chain any more
-		uint32_t consumed = lds_acquire_u32(flags + kTeamWindows * 4);
-		while (k >= kTeamWindows && consumed != kTeamStop && consumed + kTeamWindows <= k)
-		{
-			__nanosleep(40);
-			consumed = lds_acquire_u32(flags + kTeamWindows * 4);
-		}
-		if (consumed == kTeamStop)
-			break; // the chain has finished (or given up on) the stream
+		// the slot's previous window (k - kTeamWindows) must have been released by the chain
+		bool stopped = false;
+		if (k >= kTeamWindows)
+			while (!mbar_try_wait(empty + k % kTeamWindows, (k / kTeamWindows - 1u) & 1u))
+				if (atomicAdd(stop, 0u)) // (the chain has finished, or given up on, the stream)
+				{
+					stopped = true;
+					break;
+				}
+		if (__any_sync(0xffffffffu, stopped))
+			break;
 
 		const uint32_t piece = k * kTeamWindow + lane * 16;
 		const uint32_t slot = (k % kTeamWindows) * kTeamWindow + lane * 16;
@@ -140,9 +133,7 @@ __device__ void team_helper(uint32_t helper, uint32_t lane, uint32_t smem, const
 		sts_v4(smem + kTeamSmemT + 3 * kTeamTable + slot, t[0], t[1], t[2], t[3]);
 		if (mirror)
 			sts_v4(smem + kTeamSmemT + 3 * kTeamTable + kTeamRing + slot, t[0], t[1], t[2], t[3]);
-		__syncwarp();
-		if (lane == 0)
-			sts_release_u32(flags + (k % kTeamWindows) * 4, k + 1);
+		mbar_arrive(full + k % kTeamWindows); // every lane arrives for its own stores
 	}
 }
 
@@ -159,25 +150,22 @@ __device__ __forceinline__ uint32_t team_u32(uint32_t smem, uint32_t rel)
 }
 
 // windows [rel / 512, (rel + span) / 512] are built; everything below rel's window may be overwritten
-__device__ __forceinline__ void team_need(uint32_t smem, uint32_t rel, uint32_t span, uint32_t n_windows, uint32_t& have_until, uint32_t& released, uint32_t lane)
+__device__ __forceinline__ void team_need(uint8_t* base, uint32_t rel, uint32_t span, uint32_t n_windows, uint32_t& have_until, uint32_t& released)
 {
-	const uint32_t first = rel / kTeamWindow;
+	uint64_t* full = reinterpret_cast<uint64_t*>(base + kTeamSmemBars);
+	uint64_t* empty = full + kTeamWindows;
+	const uint32_t first = min(rel / kTeamWindow, n_windows);
 	uint32_t last = (rel + span) / kTeamWindow;
 	if (last >= n_windows)
 		last = n_windows ? n_windows - 1 : 0;
-	if (first > released)
-	{
-		released = first;
-		if (lane == 0)
-			sts_release_u32(smem + kTeamSmemFlags + kTeamWindows * 4, first);
-	}
 	while (have_until <= last && have_until < n_windows)
 	{
-		const uint32_t flag = smem + kTeamSmemFlags + (have_until % kTeamWindows) * 4;
-		while (lds_acquire_u32(flag) != have_until + 1)
-			__nanosleep(20);
+		mbar_wait(full + have_until % kTeamWindows, (have_until / kTeamWindows) & 1u);
 		++have_until;
 	}
+	// (a window is only released after it has been waited for: a literal channel may jump over windows nobody looked at)
+	for (; released < first && released < have_until; ++released)
+		mbar_arrive(empty + released % kTeamWindows); // every lane arrives for its own reads
 }
 
 // even bits of x (bit 2i -> bit i)
@@ -191,12 +179,13 @@ __device__ __forceinline__ uint32_t even_bits(uint32_t x)
 }
 
 // One bit-packed byte-channel: header at rel, then `groups` groups.  Returns false if the channel is malformed.
-__device__ __forceinline__ bool team_channel(uint32_t smem, uint32_t& rel, uint32_t rel_end, uint32_t groups, uint32_t hdr, uint32_t version, uint32_t ctrl,
+__device__ __forceinline__ bool team_channel(uint8_t* base, uint32_t& rel, uint32_t rel_end, uint32_t groups, uint32_t hdr, uint32_t version, uint32_t ctrl,
     uint32_t n_windows, uint32_t& have_until, uint32_t& released, uint32_t lane)
 {
+	const uint32_t smem = smem_addr(base);
 	if (rel_end - rel < hdr) // (:1376)
 		return false;
-	team_need(smem, rel, hdr + 16 * kGroupReadLimit + 8, n_windows, have_until, released, lane);
+	team_need(base, rel, hdr + 16 * kGroupReadLimit + 8, n_windows, have_until, released);
 	uint32_t sel_bits = team_u32(smem, rel);
 	rel += hdr;
 
@@ -228,8 +217,9 @@ __device__ __forceinline__ bool team_channel(uint32_t smem, uint32_t& rel, uint3
 	return !(rel_last > rel_end || rel_end - rel_last < kGroupReadLimit);
 }
 
-__device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32_t smem, int framing_status, uint32_t version, uint32_t n_windows)
+__device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint8_t* base, int framing_status, uint32_t version, uint32_t n_windows)
 {
+	const uint32_t smem = smem_addr(base);
 	const DevStream* d = T.streams + s;
 	const uint8_t* src = d->src;
 	const uint32_t size = d->src_size;
@@ -271,7 +261,7 @@ __device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32
 				{
 					if (k0 == 0)
 					{
-						team_need(smem, rel, 12, n_windows, have_until, released, lane);
+						team_need(base, rel, 12, n_windows, have_until, released);
 						c_lo = team_u32(smem, rel), c_hi = team_u32(smem, rel + 4);
 						rel += ctrl_bytes;
 					}
@@ -307,7 +297,7 @@ __device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32
 					if (k >= 32)
 						break;
 					const uint32_t ctrl = (((k < 16 ? c_lo : c_hi) >> ((k & 15u) * 2u)) & 3u);
-					if (!team_channel(smem, rel, rel_end, groups, hdr, version, ctrl, n_windows, have_until, released, lane))
+					if (!team_channel(base, rel, rel_end, groups, hdr, version, ctrl, n_windows, have_until, released, lane))
 					{
 						bad = true;
 						break;
@@ -337,8 +327,8 @@ __device__ void team_chain(const DevTables& T, uint32_t s, uint32_t lane, uint32
 			for (uint32_t b = framed ? done + 1 : 0; b <= nblocks; ++b)
 				boff[b] = kInvalidOffset;
 		T.status[d->caller_index] = status;
-		// let helpers that wait for ring space run to their end
-		sts_release_u32(smem + kTeamSmemFlags + kTeamWindows * 4, kTeamStop);
+		// helpers that wait for ring space see this and leave
+		atomicExch(reinterpret_cast<uint32_t*>(base + kTeamSmemStop), 1u);
 	}
 }
 
@@ -358,8 +348,14 @@ __global__ void __launch_bounds__(kTeamThreads) walk_team_kernel(DevTables T)
 			sts_v4(smem + kTeamSmemT + i, 0u, 0u, 0u, 0u);
 			sts_v4(smem + kTeamSmemT + 4 * kTeamTable + i, 0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u);
 		}
-		if (threadIdx.x <= kTeamWindows)
-			reinterpret_cast<volatile uint32_t*>(team_smem + kTeamSmemFlags)[threadIdx.x] = 0;
+		if (threadIdx.x == 0)
+		{
+			uint64_t* bars = reinterpret_cast<uint64_t*>(team_smem + kTeamSmemBars);
+			for (uint32_t i = 0; i < 2 * kTeamWindows; ++i)
+				mbar_init(bars + i, 32); // full: the 32 lanes of the helper that built the window; empty: the 32 lanes of the chain
+			*reinterpret_cast<uint32_t*>(team_smem + kTeamSmemStop) = 0;
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
 		__syncthreads();
 
 		const DevStream* d = T.streams + s;
@@ -369,9 +365,9 @@ __global__ void __launch_bounds__(kTeamThreads) walk_team_kernel(DevTables T)
 		const uint32_t rel_limit = (framing == 0 && d->nblocks) ? ((rel0 + d->src_size + 15u) & ~15u) : 0u;
 		const uint32_t n_windows = (rel_limit + kTeamWindow - 1) / kTeamWindow;
 		if (warp == kTeamHelpers)
-			team_chain(T, s, lane, smem, framing, version, n_windows);
+			team_chain(T, s, lane, team_smem, framing, version, n_windows);
 		else
-			team_helper(warp, lane, smem, d->src - rel0, rel_limit, n_windows);
+			team_helper(warp, lane, team_smem, d->src - rel0, rel_limit, n_windows);
 		__syncthreads();
 	}
 }

@@ -12,3 +12,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --cs
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 4 -c 1 -f -o $O/${TAG}_full python bench.py --steps 2 --warmup 1 --no-configs --no-cpu --no-e2e > $O/${TAG}_ncu_c.log 2>&1
 fi
 tail -c 600 $O/${TAG}_bench.err
+if [ -n "$EXTRA" ]; then
+timeout 300 python tools/bench_meshlet.py > $O/${TAG}_meshlet.json 2> $O/${TAG}_meshlet.err
+timeout 300 python tools/bench_filters.py > $O/${TAG}_filters.json 2> $O/${TAG}_filters.err
+timeout 300 python tools/bench_index.py > $O/${TAG}_index.json 2> $O/${TAG}_index.err
+TAG=$TAG bash tools/gpu_sanitize_r2.sh > /dev/null 2>&1
+fi
