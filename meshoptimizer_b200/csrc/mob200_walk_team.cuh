@@ -158,14 +158,18 @@ __device__ __forceinline__ void team_need(uint8_t* base, uint32_t rel, uint32_t 
 	uint32_t last = (rel + span) / kTeamWindow;
 	if (last >= n_windows)
 		last = n_windows ? n_windows - 1 : 0;
-	while (have_until <= last && have_until < n_windows)
+	for (;;)
 	{
+		// Release first, wait second: the helper that builds the window waited for below may need the slot of a window this
+		// warp has left behind (a run of literal channels jumps over several windows at once).  A window is only released
+		// after it has been waited for, so that the phases of its two barriers stay paired.
+		for (; released < first && released < have_until; ++released)
+			mbar_arrive(empty + released % kTeamWindows); // every lane arrives for its own reads
+		if (!(have_until <= last && have_until < n_windows))
+			break;
 		mbar_wait(full + have_until % kTeamWindows, (have_until / kTeamWindows) & 1u);
 		++have_until;
 	}
-	// (a window is only released after it has been waited for: a literal channel may jump over windows nobody looked at)
-	for (; released < first && released < have_until; ++released)
-		mbar_arrive(empty + released % kTeamWindows); // every lane arrives for its own reads
 }
 
 // even bits of x (bit 2i -> bit i)
