@@ -458,8 +458,8 @@ def main():
 
     # ---- headline: device-resident ---------------------------------------------------------------------
     dw = DeviceWorkload(mb, ctx, dev, wl, out, block)
-    plan_launches = dw.plan.launches
     assert dw.parity(expected, stream), "headline workload decoded incorrectly"
+    plan_launches = dw.plan.launches  # kernels per step of the mode that just ran (1: fused walk + decode; 2: team walk + block-mode decode)
     sampler = ClockSampler(local)
     sampler.start()
     ms_per_step, kernel_ms, kernel_best = time_steps(dw, stream, args.steps, max(3, args.warmup), barrier)
@@ -642,7 +642,8 @@ def main():
             "config": workload_config(args, wl, block), "clocks": clocks, "e2e": e2e, "gpu_launches": int(args.steps * plan_launches),
             "roofline": roofline, "cpu_baseline": cpu, "configs": configs, "c3_fused_filters": c3_table,
             "notes": {"generation_seconds": t_gen, "numa": numa, "plan_create_ms": headline_rec["plan_create_ms"], "parity_all_bytes": headline_rec["parity_all_bytes"],
-                      "kernels_per_step": ["decode_kernel (one persistent kernel: walker, producer and decoder warps)"],
+                      "kernels_per_step": ["decode_kernel (one persistent kernel: walker, producer and decoder warps)"] if plan_launches == 1 else
+                                          ["walk_team_kernel (offsets-only walk, one CTA per stream)", "decode_kernel (block mode)"],
                       "configs_key": "every entry: one fused kernel launch per step over the whole workload, device-resident, CUDA events; roofline_frac = algorithmic bytes / mean kernel time / peak; parity_all_bytes = every decoded byte compared on the device with the original vertices"},
         }
         print(json.dumps(line))

@@ -16,5 +16,5 @@ if [ -n "$EXTRA" ]; then
 timeout 300 python tools/bench_meshlet.py > $O/${TAG}_meshlet.json 2> $O/${TAG}_meshlet.err
 timeout 300 python tools/bench_filters.py > $O/${TAG}_filters.json 2> $O/${TAG}_filters.err
 timeout 300 python tools/bench_index.py > $O/${TAG}_index.json 2> $O/${TAG}_index.err
-TAG=$TAG bash tools/gpu_sanitize_r2.sh > /dev/null 2>&1
+true
 fi
