@@ -172,6 +172,10 @@ __device__ __forceinline__ uint32_t sum_bytes(const uint4& v)
 // producer warp
 // ------------------------------------------------------------------------------------------------
 
+#ifndef MOB200_CARRY_LAG
+#define MOB200_CARRY_LAG 1
+#endif
+constexpr uint32_t kCarryLag = MOB200_CARRY_LAG; // block mode: blocks the producer may stage ahead of the carry it is resolving (< slots in flight)
 constexpr uint32_t kProducerBatch = 16;// blocks whose metadata chains (ticket -> stream -> progress -> offsets) are in flight together, one per lane
 
 // debug counters (cycles, summed over CTAs): see mob200_plan_debug_counters
@@ -326,22 +330,26 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		// Rounds variant: the members of a round are all staged (slot, ring piece, TMA) before the carry of any of them is
 		// resolved -- the decoders start a round when every member has landed, and a carry may depend on a block that
 		// another unit decodes in a round of the same age, so a copy that waited for a carry could close a cycle.
-		// Plain form: the carry of block j is resolved after block j + 1 has been staged (a carry may have to wait for
-		// blocks that other units are still unpacking -- in block mode the predecessor is the ticket right before this
-		// one -- and the decoders should find their next block staged when it arrives).
+		// Plain form, block mode: the carry of block j is resolved after the blocks up to j + kCarryLag have been staged (a
+		// carry may have to wait for blocks that other units are still unpacking -- with one stream the predecessor is the
+		// ticket right before this one -- and the decoders should find their next blocks staged meanwhile).
 		uint32_t members = 1, g = 0, pass = 0;
 		uint32_t js = 0, jc = 0; // plain form: next block to stage / to resolve the carry of
 		for (uint32_t j0 = 0; kRounds ? j0 < in_batch : jc < in_batch;)
 		{
 			bool plain_stage = !kRounds && js < in_batch && js == jc;
-			if (!kRounds && kBlock && js < in_batch && js == jc + 1)
+			if (!kRounds && kBlock && js < in_batch && js > jc && js <= jc + kCarryLag)
 			{
-				// one block ahead of the carry -- but only if its ring piece can be had without waiting for block jc itself
-				// (whose decoders wait for the carry this warp has not resolved yet): with jc the only live piece the
-				// allocator below takes `head` if the piece fits behind it, else offset 0 if it fits in front of it
+				// up to kCarryLag blocks ahead of the carry -- but only if the ring piece of block js can be had without waiting
+				// for a block whose carry this warp has not resolved yet (its decoders wait for that carry): the pieces of
+				// the unresolved blocks jc .. js-1 are the ones in front of `head`; with everything older released, the
+				// allocator below takes `head` if the piece fits behind it, else offset 0 if it fits in front of the oldest
 				const uint32_t lens = __shfl_sync(0xffffffffu, m_len, js);
-				const uint32_t slot_c = (i0 + jc) & (kSlots - 1);
-				plain_stage = ring_len[slot_c] == 0 || head + lens <= kStageRingBytes || lens < ring_start[slot_c];
+				uint32_t so = 0xffffffffu;
+				for (uint32_t u = jc; u < js && so == 0xffffffffu; ++u)
+					if (ring_len[(i0 + u) & (kSlots - 1)])
+						so = ring_start[(i0 + u) & (kSlots - 1)];
+				plain_stage = so == 0xffffffffu || (head > so ? (head + lens <= kStageRingBytes || lens < so) : head + lens < so);
 			}
 			if (kRounds && pass == 0 && g == 0)
 			{
@@ -585,8 +593,11 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 								done = true;
 							else
 								dist += __popc(consume);
+#ifndef MOB200_LOOKBACK_SLEEP
+#define MOB200_LOOKBACK_SLEEP 64
+#endif
 							if (consume == 0)
-								__nanosleep(64);
+								__nanosleep(MOB200_LOOKBACK_SLEEP);
 						}
 					}
 					if (qon && pj == 0)
