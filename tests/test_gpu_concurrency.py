@@ -88,3 +88,32 @@ def test_host_batches_from_several_threads_with_their_own_contexts(mb):
         t.join(timeout=240)
     assert not any(t.is_alive() for t in threads), "a caller is stuck"
     assert not errors, errors[:3]
+
+
+def test_multi_device_batch_entry_point(mb):
+    """mob200_decode_batch_multi_host: LPT partition + one host thread and context per listed device (here the one GPU
+    of the test box, listed once and twice: the second form runs two shards concurrently on the same device)"""
+    import ctypes
+
+    if not loader.have_ref():
+        pytest.skip("needs the reference encoder")
+    w = workloads.merge("mixed", [workloads.c2(total=1 << 17, seg=1 << 13), workloads.c3("quat12", count=60_000, seg=7_000), workloads.c4(500)])
+    want = workloads.expected_outputs(w)
+    port = loader.port()
+    sidecars = [port.block_offsets(int(w.counts[i]), int(w.vertex_sizes[i]), w.stream(i))[1] for i in range(w.n)]
+    for devices, with_side in (([0], False), ([0, 0], True)):
+        outs = [np.zeros(max(1, int(w.counts[i]) * int(w.vertex_sizes[i])), np.uint8) for i in range(w.n)]
+        srcs = [np.ascontiguousarray(w.stream(i)) for i in range(w.n)]
+        arr = mb.make_streams([(srcs[i].ctypes.data, srcs[i].size, outs[i].ctypes.data, int(w.counts[i]), int(w.vertex_sizes[i]), int(w.filters[i])) for i in range(w.n)])
+        side = None
+        if with_side:
+            side = (ctypes.c_void_p * w.n)()
+            for i, sc in enumerate(sidecars):
+                side[i] = sc.ctypes.data if sc.size else None
+        devs = (ctypes.c_int * len(devices))(*devices)
+        ms = (ctypes.c_float * len(devices))()
+        rc = mb.lib().mob200_decode_batch_multi_host(devs, len(devices), arr, w.n, side, ms)
+        assert rc == 0 and all(arr[i].status == 0 for i in range(w.n))
+        for i in range(w.n):
+            nb = int(w.counts[i]) * int(w.vertex_sizes[i])
+            assert np.array_equal(outs[i][:nb], want[i]), (devices, i)
