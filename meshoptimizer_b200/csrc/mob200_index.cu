@@ -12,6 +12,7 @@
 #include "mob200_host.h"
 
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -244,11 +245,18 @@ __device__ int decode_sequence(const DevIndexStream& s)
 	return data == safe_end ? 0 : -3;
 }
 
+// kSparse = false: one stream per THREAD (many streams: a warp's 32 lanes each follow their own stream, diverging freely;
+//                  throughput comes from the number of streams).
+// kSparse = true:  one stream per WARP, lane 0 alone runs the state machine (few long streams: the 32 lanes of a warp
+//                  that each follow another branch of another stream execute one after the other, so a long list decoded
+//                  next to 31 others runs at 1/32 of a warp's speed; alone on its warp it never diverges).
+template <bool kSparse>
 __global__ void __launch_bounds__(kIndexThreads) index_decode_kernel(const DevIndexStream* streams, int32_t* status, uint32_t n)
 {
 	__shared__ uint32_t fifo[48 * kIndexThreads];
-	const uint32_t i = blockIdx.x * kIndexThreads + threadIdx.x;
-	if (i >= n)
+	const uint32_t slot = kSparse ? threadIdx.x >> 5 : threadIdx.x;
+	const uint32_t i = kSparse ? blockIdx.x * (kIndexThreads / 32) + slot : blockIdx.x * kIndexThreads + threadIdx.x;
+	if (i >= n || (kSparse && (threadIdx.x & 31u)))
 		return;
 	const DevIndexStream s = streams[i];
 	int rc;
@@ -256,9 +264,9 @@ __global__ void __launch_bounds__(kIndexThreads) index_decode_kernel(const DevIn
 	{
 		IndexFifos F;
 		F.stride = kIndexThreads;
-		F.vf = fifo + threadIdx.x;
-		F.ea = fifo + 16 * kIndexThreads + threadIdx.x;
-		F.eb = fifo + 32 * kIndexThreads + threadIdx.x;
+		F.vf = fifo + slot;
+		F.ea = fifo + 16 * kIndexThreads + slot;
+		F.eb = fifo + 32 * kIndexThreads + slot;
 		F.vo = F.eo = 0;
 		rc = decode_triangles(s, F);
 	}
@@ -327,7 +335,18 @@ int run_index_batch(mob200_Context* ctx, mob200_IndexStream* streams, size_t n, 
 		void* d_desc = scratch.ptr;
 		int32_t* d_status = reinterpret_cast<int32_t*>(static_cast<uint8_t*>(d_desc) + desc_bytes);
 		CUDA_TRY(cudaMemcpyAsync(d_desc, host.data(), desc_bytes, cudaMemcpyHostToDevice, st));
-		index_decode_kernel<<<(unsigned)((m + kIndexThreads - 1) / kIndexThreads), kIndexThreads, 0, st>>>(static_cast<const DevIndexStream*>(d_desc), d_status, (uint32_t)m);
+		// few long streams: one warp each (at most one wave of warps on the device); else one thread each
+		size_t total_indices = 0;
+		for (size_t k = 0; k < m; ++k)
+			total_indices += host[k].index_count;
+		int sms = 148;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx ? ctx->device : 0);
+		static const int form = getenv("MOB200_INDEX_FORM") ? atoi(getenv("MOB200_INDEX_FORM")) : -1;
+		const bool sparse = form >= 0 ? form == 1 : (m <= (size_t)sms * 32 && total_indices / m >= 3 * 1024);
+		if (sparse)
+			index_decode_kernel<true><<<(unsigned)((m + kIndexThreads / 32 - 1) / (kIndexThreads / 32)), kIndexThreads, 0, st>>>(static_cast<const DevIndexStream*>(d_desc), d_status, (uint32_t)m);
+		else
+			index_decode_kernel<false><<<(unsigned)((m + kIndexThreads - 1) / kIndexThreads), kIndexThreads, 0, st>>>(static_cast<const DevIndexStream*>(d_desc), d_status, (uint32_t)m);
 		CUDA_TRY(cudaGetLastError());
 		std::vector<int32_t> rc(m);
 		CUDA_TRY(cudaMemcpyAsync(rc.data(), d_status, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
