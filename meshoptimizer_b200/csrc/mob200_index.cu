@@ -98,10 +98,7 @@ struct IndexFifos
 };
 
 // triangle list (reference meshopt_decodeIndexBuffer, :384-576)
-// lead = 0: one thread per stream.  lead = lane + 1: the whole warp follows ONE stream in step (every lane holds the same
-// state, so nothing diverges); lane 0 stores, and every 32 triangles each lane prefetches one 128-byte line ahead of the code
-// cursor (lanes 0-7) or the data cursor (lanes 8-31) into L1, so that the byte loads of the chain hit.
-__device__ int decode_triangles(const DevIndexStream& s, IndexFifos F, uint32_t lead)
+__device__ int decode_triangles(const DevIndexStream& s, IndexFifos F)
 {
 	const uint8_t* src = s.src;
 	const uint32_t size = s.src_size;
@@ -130,16 +127,8 @@ __device__ int decode_triangles(const DevIndexStream& s, IndexFifos F, uint32_t 
 	const uint32_t safe_end = size - 16; // ... and ends where the 16-byte codeaux table starts
 	const uint32_t table = safe_end;
 
-	const bool store = lead <= 1;
 	for (uint32_t t = 0; t < tris; ++t)
 	{
-		if (lead && (t & 31u) == 0)
-		{
-			const uint32_t lane = lead - 1;
-			const uint32_t ahead = lane < 8 ? 1 + t + 128u * (lane + 1) : data + 128u * (lane - 7);
-			if (ahead < size)
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(src + ahead));
-		}
 		const uint32_t code = __ldg(src + 1 + t);
 		uint32_t a, b, c;
 		if (code < 0xf0u)
@@ -214,14 +203,13 @@ __device__ int decode_triangles(const DevIndexStream& s, IndexFifos F, uint32_t 
 			F.push_edge(c, b);
 			F.push_edge(a, c);
 		}
-		if (store)
-			index_store3(s.dst, s.index_size, t, a, b, c);
+		index_store3(s.dst, s.index_size, t, a, b, c);
 	}
 	return data == safe_end ? 0 : -3;
 }
 
 // index sequence (reference meshopt_decodeIndexSequence, :647-703)
-__device__ int decode_sequence(const DevIndexStream& s, uint32_t lead)
+__device__ int decode_sequence(const DevIndexStream& s)
 {
 	const uint8_t* src = s.src;
 	const uint32_t size = s.src_size;
@@ -236,15 +224,8 @@ __device__ int decode_sequence(const DevIndexStream& s, uint32_t lead)
 	uint32_t data = 1;
 	const uint32_t safe_end = size - 4;
 	uint32_t last0 = 0, last1 = 0;
-	const bool store = lead <= 1;
 	for (uint32_t i = 0; i < s.index_count; ++i)
 	{
-		if (lead && (i & 63u) == 0)
-		{
-			const uint32_t ahead = data + 128u * lead;
-			if (ahead < size)
-				asm volatile("prefetch.global.L1 [%0];" ::"l"(src + ahead));
-		}
 		if (data >= safe_end)
 			return -2;
 		uint32_t v = index_varint(src, data);
@@ -256,8 +237,6 @@ __device__ int decode_sequence(const DevIndexStream& s, uint32_t lead)
 			last1 = index;
 		else
 			last0 = index;
-		if (!store)
-			continue;
 		if (s.index_size == 2)
 			reinterpret_cast<uint16_t*>(s.dst)[i] = (uint16_t)index;
 		else
@@ -268,19 +247,17 @@ __device__ int decode_sequence(const DevIndexStream& s, uint32_t lead)
 
 // kSparse = false: one stream per THREAD (many streams: a warp's 32 lanes each follow their own stream, diverging freely;
 //                  throughput comes from the number of streams).
-// kSparse = true:  one stream per WARP (few long streams: the 32 lanes of a warp that each follow another branch of
-//                  another stream execute one after the other, so a long list decoded next to 31 others runs at 1/32 of a
-//                  warp's speed).  All 32 lanes run the same state machine on the same stream (no divergence; the FIFO
-//                  slots get the same value from every lane), lane 0 stores, the others prefetch the input ahead.
+// kSparse = true:  one stream per WARP, lane 0 alone runs the state machine (few long streams: the 32 lanes of a warp
+//                  that each follow another branch of another stream execute one after the other, so a long list decoded
+//                  next to 31 others runs at 1/32 of a warp's speed; alone on its warp it never diverges).
 template <bool kSparse>
 __global__ void __launch_bounds__(kIndexThreads) index_decode_kernel(const DevIndexStream* streams, int32_t* status, uint32_t n)
 {
 	__shared__ uint32_t fifo[48 * kIndexThreads];
 	const uint32_t slot = kSparse ? threadIdx.x >> 5 : threadIdx.x;
 	const uint32_t i = kSparse ? blockIdx.x * (kIndexThreads / 32) + slot : blockIdx.x * kIndexThreads + threadIdx.x;
-	if (i >= n)
+	if (i >= n || (kSparse && (threadIdx.x & 31u)))
 		return;
-	const uint32_t lead = kSparse ? (threadIdx.x & 31u) + 1u : 0u;
 	const DevIndexStream s = streams[i];
 	int rc;
 	if (s.kind == MOB200_INDEX_TRIANGLES)
@@ -291,12 +268,11 @@ __global__ void __launch_bounds__(kIndexThreads) index_decode_kernel(const DevIn
 		F.ea = fifo + 16 * kIndexThreads + slot;
 		F.eb = fifo + 32 * kIndexThreads + slot;
 		F.vo = F.eo = 0;
-		rc = decode_triangles(s, F, lead);
+		rc = decode_triangles(s, F);
 	}
 	else
-		rc = decode_sequence(s, lead);
-	if (lead <= 1)
-		status[i] = rc;
+		rc = decode_sequence(s);
+	status[i] = rc;
 }
 
 } // namespace mob200
