@@ -40,6 +40,9 @@ struct mob200_Plan
 	bool have_offsets = false;
 	int wide_walk_choice = 0, rounds_choice = 0;
 	bool small_blocks_majority = false;
+	const uint2* tickets_level = nullptr; // decode order of the fused walk: level-major inside a wave of streams
+	const uint2* tickets_runs = nullptr;  // block mode + rounds: runs of 1 << run_shift consecutive blocks of a stream (small-vertex plans only)
+	uint32_t run_shift = 0;
 	bool two_phase = false; // the last run was a team walk + block-mode decode (two launches)
 	// ring of CUDA-event pairs (before / after the fused walk + decode kernel), one per run, recorded on the
 	// launching stream: per-launch durations can be read back after a timed region without any
@@ -79,6 +82,8 @@ extern "C" int mob200_context_create(mob200_Context** out, int device)
 		ctx->wide_walk_mode = atoi(wide);
 	if (const char* team = getenv("MOB200_TEAM_WALK"))
 		ctx->team_walk = atoi(team);
+	if (const char* rm = getenv("MOB200_RUN_MAJOR"))
+		ctx->run_major = atoi(rm);
 	if (const char* rounds = getenv("MOB200_ROUNDS"))
 		ctx->rounds_mode = atoi(rounds);
 	if (const char* lead = getenv("MOB200_WALKER_LEAD"))
@@ -194,7 +199,7 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 
 	std::vector<DevStream> host(n);
 	size_t n_with_blocks = 0;
-	uint64_t total_blocks = 0, total_chan = 0, small_blocks = 0; // small: a block of <= 12-byte vertices (one or two work quanta of the decoders; 16-byte blocks gain nothing from rounds)
+	uint64_t total_blocks = 0, total_chan = 0, small_blocks = 0, tiny_blocks = 0; // small: a block of <= 12-byte vertices (one or two work quanta of the decoders; 16-byte blocks gain nothing from rounds)
 	for (size_t i = 0; i < n; ++i)
 	{
 		const mob200_Stream& s = streams[order[i]];
@@ -214,6 +219,7 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 			n_with_blocks = i + 1;
 		total_blocks += d.nblocks;
 		small_blocks += s.vertex_size <= 12 ? d.nblocks : 0;
+		tiny_blocks += s.vertex_size <= 8 ? d.nblocks : 0; // one work quantum: four of them make a decode round
 		total_chan += (uint64_t)d.nblocks * s.vertex_size;
 		if (total_blocks >= 0xfffffff0ull)
 			return MOB200_ERR_ARGUMENT;
@@ -253,6 +259,27 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 		}
 	}
 
+	// block mode + rounds: the order is free of the walkers (every block is walked on its own), so the four blocks that
+	// share a decode round are four CONSECUTIVE blocks of one stream: inside a round the carries chain through the unit's
+	// own look-back entries, and the first member's predecessor lies four times as many tickets back
+	const bool small_majority = small_blocks * 2 > total_blocks;
+	const uint32_t run_shift = tiny_blocks * 2 > small_blocks ? kRunShiftMax : 1u, kRunBlocks = 1u << run_shift;
+	std::vector<uint2> ticket_runs(small_majority ? total_blocks : 0);
+	if (small_majority)
+	{
+		size_t t = 0;
+		const uint32_t levels = n ? host[0].nblocks : 0; // sorted: the first stream is the longest
+		size_t live = n;
+		for (uint32_t b0 = 0; b0 < levels; b0 += kRunBlocks)
+		{
+			while (live > 0 && host[live - 1].nblocks <= b0)
+				--live;
+			for (size_t i = 0; i < live; ++i)
+				for (uint32_t b = b0; b < std::min<uint32_t>(b0 + kRunBlocks, host[i].nblocks); ++b)
+					ticket_runs[t++] = make_uint2((uint32_t)i, b);
+		}
+	}
+
 	// one arena for every table
 	size_t off_streams = 0;
 	size_t off_boff = align_up(off_streams + n * sizeof(DevStream), 256);
@@ -260,9 +287,14 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	size_t off_ready = align_up(off_table + total_chan * 32, 256);
 	size_t off_look = align_up(off_ready + total_blocks * 4, 256);
 	size_t off_tinfo = align_up(off_look + (total_chan / 4) * 8, 256);
-	size_t off_status = align_up(off_tinfo + total_blocks * 8, 256);
+	size_t off_truns = align_up(off_tinfo + total_blocks * 8, 256);
+	size_t off_status = align_up(off_truns + ticket_runs.size() * 8, 256);
 	size_t off_counters = align_up(off_status + n * 4, 256);
+#ifdef MOB200_TRACE
+	size_t arena_bytes = off_counters + 256 + 16384 * 8; // event trace of one unit (diagnostics build)
+#else
 	size_t arena_bytes = off_counters + 256;
+#endif
 
 	if (ext_arena)
 	{
@@ -287,6 +319,10 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.block_ready = reinterpret_cast<uint32_t*>(base + off_ready);
 	plan->T.lookback = reinterpret_cast<unsigned long long*>(base + off_look);
 	plan->T.ticket_info = reinterpret_cast<uint2*>(base + off_tinfo);
+	plan->tickets_level = plan->T.ticket_info;
+	plan->tickets_runs = small_majority ? reinterpret_cast<uint2*>(base + off_truns) : nullptr;
+	plan->T.ticket_shift = 0;
+	plan->run_shift = run_shift;
 	plan->T.status = reinterpret_cast<int32_t*>(base + off_status);
 	plan->T.counters = reinterpret_cast<uint32_t*>(base + off_counters);
 	plan->T.n_streams = (uint32_t)n;
@@ -320,12 +356,14 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	cudaStream_t st = init_stream;
 	ok = ok && cudaMemsetAsync(base + off_ready, 0, total_blocks * 4, st) == cudaSuccess;      // epoch 0 = never published
 	ok = ok && cudaMemsetAsync(base + off_look, 0, (total_chan / 4) * 8, st) == cudaSuccess;
-	ok = ok && cudaMemsetAsync(base + off_counters, 0, 256, st) == cudaSuccess;
+	ok = ok && cudaMemsetAsync(base + off_counters, 0, arena_bytes - off_counters, st) == cudaSuccess;
 	if (n)
 		ok = ok && cudaMemcpyAsync(base + off_streams, host.data(), n * sizeof(DevStream), cudaMemcpyHostToDevice, st) == cudaSuccess;
 	if (total_blocks)
 	{
 		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
+		if (small_majority)
+			ok = ok && cudaMemcpyAsync(base + off_truns, ticket_runs.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
 	}
 	std::vector<uint32_t> side;
 	if (sidecars)
@@ -521,6 +559,11 @@ extern "C" int mob200_plan_run_ex(mob200_Plan* plan, void* cuda_stream, int flag
 			T.rounds = plan->small_blocks_majority && plan->T.total_blocks >= 8u * plan->grid ? 1u : 0u;
 	}
 	plan->two_phase = two_phase;
+	const bool run_major = T.block_mode && T.rounds && plan->tickets_runs && plan->ctx->run_major;
+	T.ticket_info = run_major ? plan->tickets_runs : plan->tickets_level;
+	T.ticket_shift = run_major ? plan->run_shift : 0u;
+	if (two_phase)
+		Twalk.ticket_info = plan->tickets_level, Twalk.ticket_shift = 0;
 
 	cudaEvent_t* ev = plan->ev[plan->runs % mob200_Plan::kRing];
 	const bool timed = ev[0] != nullptr;
@@ -578,6 +621,21 @@ extern "C" int mob200_plan_debug_counters(mob200_Plan* plan, unsigned long long*
 		CUDA_TRY(cudaMemset(plan->T.counters + 16, 0, 16 * sizeof(unsigned long long)));
 	return 0;
 }
+
+#ifdef MOB200_TRACE
+// diagnostics build only: the event trace of unit MOB200_TRACE_UNIT (entry 0 = events recorded); reset afterwards
+extern "C" __attribute__((visibility("default"))) int mob200_plan_debug_trace(mob200_Plan* plan, unsigned long long* out, int count)
+{
+	if (!plan || !out || count < 1 || count > 16384)
+		return MOB200_ERR_ARGUMENT;
+	if (set_device(plan->ctx))
+		return MOB200_ERR_CUDA;
+	CUDA_TRY(cudaDeviceSynchronize());
+	CUDA_TRY(cudaMemcpy(out, plan->T.counters + 64, (size_t)count * 8, cudaMemcpyDeviceToHost));
+	CUDA_TRY(cudaMemset(plan->T.counters + 64, 0, 16384 * 8));
+	return 0;
+}
+#endif
 
 extern "C" int mob200_plan_status(mob200_Plan* plan, int* status, void* cuda_stream)
 {

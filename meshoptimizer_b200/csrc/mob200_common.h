@@ -18,6 +18,8 @@ constexpr uint32_t kGroupReadLimit = 24;   // bytes that must remain readable be
 constexpr uint32_t kTailMinV0 = 32;
 constexpr uint32_t kTailMinV1 = 24;
 
+constexpr uint32_t kRunShiftMax = 2; // run-major decode order: 1 << shift consecutive blocks of a stream per ticket chunk (= the blocks of a decode round:
+                                     // four of <= 8-byte vertices, two of 12- / 16-byte vertices)
 constexpr uint32_t kInvalidOffset = 0xffffffffu; // walk result for a block that must not be decoded
 
 // largest encoded size of one block over all legal vertex sizes (vs = 256: 256*(1+2*24)+64 = 12608)
@@ -94,6 +96,10 @@ struct DevTables
 	uint32_t block_mode;          // 1: block_offset is an INPUT (a block-offset sidecar: caller-provided, or kept from an earlier run):
 	                              // every block is walked on its own by one walker lane, which also checks that the block ends where
 	                              // the next one is said to start -- a stale sidecar is detected, never trusted (kStatusSidecar)
+	uint32_t ticket_shift;        // log2 of the ticket chunk: unit u takes tickets in chunks of 1 << ticket_shift (chunk c of the order goes to
+	                              // unit c % units).  0 with the level-major order; 2 with the run-major order of block mode + rounds,
+	                              // where a chunk is four consecutive blocks of one stream: they share a decode round, so only the first
+	                              // of them looks back across units
 	uint32_t keep_status;         // block mode after the team walk: the status words already hold the reference codes; only a
 	                              // stream that is still 0 may be marked kStatusSidecar
 };

@@ -52,13 +52,14 @@ struct BlockParams // written by the producer, read by the decoders after the sl
 	const uint16_t* rows_global;
 	unsigned long long* lookback; // this block's entries (vs/4 of them); predecessors lie vs/4 entries lower each
 	uint32_t round_members;       // rounds variant: > 0: this block opens a decode round of so many consecutive blocks; 0: it continues one
-	uint32_t pad;
+	uint32_t chain;               // rounds variant, on a round's first block: 1 = the members are consecutive blocks of ONE stream (run-major
+	                              // order): the producer resolves the carry of the first member only, the decoder warps chain the others
 };
 
 struct SlotData
 {
 	BlockParams P;          // 80 bytes
-	uint32_t pad[4];
+	uint32_t chain_total[4]; // chained round: this block's aggregate per 4-byte lane (vertex sizes <= 16), written by its decoder warp
 	uint32_t carry[64];     // per 4-byte lane: value of the vertex before the block
 	uint8_t channels[64];   // per 4-byte lane: channel byte (v1) or 0
 };
@@ -176,7 +177,12 @@ __device__ __forceinline__ uint32_t sum_bytes(const uint4& v)
 #define MOB200_CARRY_LAG 1
 #endif
 constexpr uint32_t kCarryLag = MOB200_CARRY_LAG; // block mode: blocks the producer may stage ahead of the carry it is resolving (< slots in flight)
+#ifndef MOB200_ROUND_LAG
+#define MOB200_ROUND_LAG 0
+#endif
+constexpr uint32_t kRoundLag = MOB200_ROUND_LAG; // rounds form, block mode: rounds staged ahead of the oldest unresolved carry (0 or 1)
 constexpr uint32_t kProducerBatch = 16;// blocks whose metadata chains (ticket -> stream -> progress -> offsets) are in flight together, one per lane
+static_assert(kRoundBlocks == (1u << kRunShiftMax) && kProducerBatch % kRoundBlocks == 0, "a ticket chunk (one run of a stream) must not straddle two metadata batches");
 
 // debug counters (cycles, summed over CTAs): see mob200_plan_debug_counters
 enum
@@ -196,6 +202,24 @@ __device__ __forceinline__ unsigned long long* debug_counters(const DevTables& T
 	return reinterpret_cast<unsigned long long*>(T.counters + 16);
 }
 
+// The decode order is dealt to the units in chunks of 1 << ticket_shift tickets, chunk c to unit c % units.
+__device__ __forceinline__ uint32_t unit_block_count(const DevTables& T, uint32_t unit)
+{
+	const uint32_t sh = T.ticket_shift;
+	const uint32_t chunks = (T.total_blocks + (1u << sh) - 1u) >> sh;
+	if (unit >= chunks)
+		return 0u;
+	const uint32_t mine = (chunks - unit + T.units - 1) / T.units;
+	const uint32_t last = unit + (mine - 1) * T.units; // the last chunk of the order may be short
+	return (mine << sh) - (last == chunks - 1 ? (chunks << sh) - T.total_blocks : 0u);
+}
+
+__device__ __forceinline__ uint32_t unit_ticket(const DevTables& T, uint32_t unit, uint32_t i)
+{
+	const uint32_t sh = T.ticket_shift;
+	return ((((i >> sh) * T.units) + unit) << sh) + (i & ((1u << sh) - 1u));
+}
+
 template <bool kRounds, bool kBlock>
 __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t unit)
 {
@@ -212,7 +236,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 
 	uint32_t head = 0;  // next free byte of the staging ring
 	uint32_t freed = 0; // blocks [freed, i) of this CTA's sequence are in flight (their ring pieces are live)
-	const uint32_t my_count = unit < T.total_blocks ? (T.total_blocks - unit + T.units - 1) / T.units : 0u;
+	const uint32_t my_count = unit_block_count(T, unit);
 
 	long long dbg_meta = 0, dbg_slot = 0, dbg_look = 0;
 	const long long dbg_t0 = dbg_clock();
@@ -221,12 +245,14 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 	{
 		// ---- metadata of up to kProducerBatch blocks, one per lane: the dependent global loads of all of them overlap ----
 		const long long c0 = dbg_clock();
+		MOB200_TRACE_EVENT(T, unit, lane, 1, i0);
 		// level 1: ticket -> (stream, block); level 2: stream descriptor + walker progress (which also carries the codec
 		// version); level 3: block byte range, channel bytes, and -- four entries per lane, two lanes per block -- the
 		// look-back entries of the predecessor block.  Everything of one level is requested before any of it is used.
 		const uint32_t mi = i0 + lane;
 		const bool has = lane < kProducerBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0, m_ready = 0;
+		uint32_t m_s = 0xffffffffu; // stream of the block (chained rounds)
 		uint32_t m_quanta = 0, m_len = 0; // rounds variant: decoder work quanta (32 items each) and staged bytes of the block
 		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
 		const uint32_t* boff = nullptr;
@@ -234,10 +260,11 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		uint32_t src_size = 0;
 		if (has)
 		{
-			const uint32_t t = unit + mi * T.units;
+			const uint32_t t = unit_ticket(T, unit, mi);
 			const uint2 info = __ldg(T.ticket_info + t);
 			const uint32_t s = info.x, b = info.y;
 			const DevStream* d = T.streams + s;
+			m_s = s;
 			src = d->src;
 			src_size = d->src_size;
 			const uint32_t vs = d->vertex_size;
@@ -324,6 +351,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		}
 		__syncwarp();
 		dbg_meta += dbg_clock() - c0;
+		MOB200_TRACE_EVENT(T, unit, lane, 2, i0);
 
 		// ---- hand the blocks to the decoders, in order -------------------------------------------------------------
 		const uint32_t in_batch = min(kProducerBatch, my_count - i0);
@@ -333,10 +361,17 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		// Plain form, block mode: the carry of block j is resolved after the blocks up to j + kCarryLag have been staged (a
 		// carry may have to wait for blocks that other units are still unpacking -- with one stream the predecessor is the
 		// ticket right before this one -- and the decoders should find their next blocks staged meanwhile).
-		uint32_t members = 1, g = 0, pass = 0;
-		uint32_t js = 0, jc = 0; // plain form: next block to stage / to resolve the carry of
-		for (uint32_t j0 = 0; kRounds ? j0 < in_batch : jc < in_batch;)
+		// Rounds form, block mode: the same one round ahead (kRoundLag) -- round N is staged while the carries of the round
+		// before it (A) are still open, if its ring pieces can be had without waiting for A's.
+		uint32_t g = 0, mode = 0;   // rounds form: 0 decide, 1 staging round N, 2 resolving the carries of round A
+		uint32_t sj = 0;            // rounds form: next block of the batch to stage
+		uint32_t n_j0 = 0, n_members = 1, a_j0 = 0, a_members = 0;
+		bool n_chained = false, n_wait = false, a_chained = false, a_have = false;
+		uint32_t js = 0, jc = 0;    // plain form: next block to stage / to resolve the carry of
+		for (;;)
 		{
+			if (!kRounds && jc >= in_batch)
+				break;
 			bool plain_stage = !kRounds && js < in_batch && js == jc;
 			if (!kRounds && kBlock && js < in_batch && js > jc && js <= jc + kCarryLag)
 			{
@@ -351,34 +386,97 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						so = ring_start[(i0 + u) & (kSlots - 1)];
 				plain_stage = so == 0xffffffffu || (head > so ? (head + lens <= kStageRingBytes || lens < so) : head + lens < so);
 			}
-			if (kRounds && pass == 0 && g == 0)
+			if (kRounds && mode == 0)
 			{
-				// a block of at most two work quanta is joined by the following blocks of this batch as long as the round
-				// stays within the four decoder warps and within half of the staging ring (all members are staged together)
-				uint32_t qs = __shfl_sync(0xffffffffu, m_quanta, j0);
-				members = 1;
-				if (qs <= 2)
+				g = 0;
+				if (sj < in_batch && !n_wait)
 				{
-					uint32_t bs = __shfl_sync(0xffffffffu, m_len, j0);
-					bool open = true;
-#pragma unroll 1
-					for (uint32_t k = 1; k < kRoundBlocks && open && j0 + k < in_batch; ++k)
+					// a block of at most two work quanta is joined by the following blocks of this batch as long as the round
+					// stays within the four decoder warps and within half of the staging ring (all members are staged together)
+					const uint32_t j0 = sj;
+					uint32_t qs = __shfl_sync(0xffffffffu, m_quanta, j0);
+					uint32_t members = 1;
+					if (qs <= 2)
 					{
-						const uint32_t qn = __shfl_sync(0xffffffffu, m_quanta, (j0 + k) & 31u), bn = __shfl_sync(0xffffffffu, m_len, (j0 + k) & 31u);
-						if (qs + qn <= kDecodeThreads / 32 && bs + bn <= kStageRingBytes / 2)
+						uint32_t bs = __shfl_sync(0xffffffffu, m_len, j0);
+						bool open = true;
+#pragma unroll 1
+						for (uint32_t k = 1; k < kRoundBlocks && open && j0 + k < in_batch; ++k)
 						{
-							qs += qn, bs += bn;
-							members = k + 1;
-							open = qs <= 2;
+							const uint32_t qn = __shfl_sync(0xffffffffu, m_quanta, (j0 + k) & 31u), bn = __shfl_sync(0xffffffffu, m_len, (j0 + k) & 31u);
+							if (qs + qn <= kDecodeThreads / 32 && bs + bn <= kStageRingBytes / 2)
+							{
+								qs += qn, bs += bn;
+								members = k + 1;
+								open = qs < kDecodeThreads / 32;
+							}
+							else
+								open = false;
 						}
-						else
-							open = false;
 					}
+					// run-major order: members that are consecutive decodable blocks of one stream (<= 16-byte vertices) chain their
+					// carries among the decoder warps; only the first member's carry comes from the look-back
+					bool chained = false;
+					if (kBlock && T.ticket_shift && members > 1)
+					{
+						const uint32_t s0 = __shfl_sync(0xffffffffu, m_s, j0), b0 = __shfl_sync(0xffffffffu, m_b, j0);
+						chained = __shfl_sync(0xffffffffu, m_valid, j0) != 0 && __shfl_sync(0xffffffffu, m_vs, j0) <= 16;
+						for (uint32_t k = 1; k < members; ++k)
+							chained = chained && __shfl_sync(0xffffffffu, m_valid, (j0 + k) & 31u) != 0 && __shfl_sync(0xffffffffu, m_s, (j0 + k) & 31u) == s0 &&
+							          __shfl_sync(0xffffffffu, m_b, (j0 + k) & 31u) == b0 + k;
+					}
+					n_j0 = j0, n_members = members, n_chained = chained;
+
+					bool ahead = !a_have;
+					if (kBlock && kRoundLag && a_have)
+					{
+						// Round A's decoders wait for carries this warp has not resolved: staging N must not wait for A's ring
+						// pieces.  Everything older than A finishes on its own: wait for it, then A's pieces are the only live
+						// ones and the allocator's choices for N's pieces can be played through exactly.
+						const uint32_t a_i0 = i0 + a_j0;
+						while (freed < a_i0)
+						{
+							mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 400);
+							++freed;
+						}
+						uint32_t so = 0xffffffffu;
+						for (uint32_t u = 0; u < a_members && so == 0xffffffffu; ++u)
+							if (ring_len[(a_i0 + u) & (kSlots - 1)])
+								so = ring_start[(a_i0 + u) & (kSlots - 1)];
+						ahead = true;
+						uint32_t h = head;
+						for (uint32_t k = 0; k < members && ahead && so != 0xffffffffu; ++k)
+						{
+							const uint32_t len = __shfl_sync(0xffffffffu, m_len, (j0 + k) & 31u);
+							if (len == 0)
+								continue;
+							if (h > so)
+							{
+								if (h + len <= kStageRingBytes)
+									h += len;
+								else if (len < so)
+									h = len;
+								else
+									ahead = false;
+							}
+							else if (h + len < so)
+								h += len;
+							else
+								ahead = false;
+						}
+					}
+					mode = ahead ? 1u : 2u;
 				}
+				else if (a_have)
+					mode = 2;
+				else
+					break;
 			}
-			const uint32_t j = kRounds ? j0 + g : (plain_stage ? js : jc);
+			const uint32_t members = mode == 1 ? n_members : a_members;
+			const bool chained = mode == 1 ? n_chained : a_chained;
+			const uint32_t j = kRounds ? (mode == 1 ? n_j0 : a_j0) + g : (plain_stage ? js : jc);
 			const uint32_t round_members = g == 0 ? members : 0u;
-			const bool do_stage = kRounds ? pass == 0 : plain_stage, do_carry = kRounds ? pass == 1 : !plain_stage;
+			const bool do_stage = kRounds ? mode == 1 : plain_stage, do_carry = kRounds ? mode == 2 : !plain_stage;
 			const uint32_t i = i0 + j;
 			const uint32_t slot = i & (kSlots - 1);
 			SlotData& S = slots[slot];
@@ -391,20 +489,36 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 
 			if (do_stage)
 			{
-				// the slot's previous block (i - kSlots) must have been unpacked by every decoder warp
+				// Blocks j .. j + cnt - 1 are staged in ONE pass, each by the lane that holds its metadata (rounds form: all
+				// members of the round; the producer's code runs once per round, not once per block -- its instructions are
+				// cold in the instruction cache every time, which is what a small-vertex round used to spend its time on).
+				const uint32_t cnt = kRounds ? members : 1u;
+				const bool owner = lane >= j && lane < j + cnt;
+				const uint32_t i_l = i0 + lane, slot_l = i_l & (kSlots - 1);
+				SlotData& Sl = slots[slot_l];
 				const long long c1 = dbg_clock();
-				mbar_wait_long(empty + slot, ((i / kSlots) & 1u) ^ 1u, 400);
-				if (i >= kSlots && freed < i - (kSlots - 1))
-					freed = i - (kSlots - 1);
+				MOB200_TRACE_EVENT(T, unit, lane, 3, i);
+				// a slot's previous block (i - kSlots) must have been unpacked by every decoder warp
+				if (owner)
+					mbar_wait_long(empty + slot_l, ((i_l / kSlots) & 1u) ^ 1u, 400);
+				__syncwarp();
+				MOB200_TRACE_EVENT(T, unit, lane, 7, i);
+				const uint32_t i_last = i + cnt - 1;
+				if (i_last >= kSlots && freed < i_last - (kSlots - 1))
+					freed = i_last - (kSlots - 1);
 
-				if (valid)
+				// ring bytes of the pass (an undecodable block takes none) and of the blocks in front of this lane's
+				uint32_t total = 0, before = 0;
+				for (uint32_t k = 0; k < cnt; ++k)
 				{
-					const uint32_t enc_bytes = __shfl_sync(0xffffffffu, m_enc, j);
-					const uint32_t rows_bytes = vs <= kRowsInRingMaxVs ? 32u * vs : 0u;
-					const uint32_t len = enc_bytes + rows_bytes;
-
-					// allocate `len` contiguous bytes of the ring (pieces are freed in order)
-					uint32_t start;
+					const uint32_t l = __shfl_sync(0xffffffffu, m_len, (j + k) & 31u);
+					before += j + k < lane ? l : 0u;
+					total += l;
+				}
+				uint32_t start = 0;
+				if (total)
+				{
+					// allocate `total` contiguous bytes of the ring (pieces are freed in order)
 					for (;;)
 					{
 						uint32_t f = freed; // oldest live piece
@@ -418,18 +532,18 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						const uint32_t so = ring_start[f & (kSlots - 1)];
 						if (head > so)
 						{
-							if (head + len <= kStageRingBytes)
+							if (head + total <= kStageRingBytes)
 							{
 								start = head;
 								break;
 							}
-							if (len < so)
+							if (total < so)
 							{
 								start = 0;
 								break;
 							}
 						}
-						else if (head + len < so)
+						else if (head + total < so)
 						{
 							start = head;
 							break;
@@ -437,80 +551,84 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						mbar_wait_long(empty + (freed & (kSlots - 1)), (freed / kSlots) & 1u, 400);
 						++freed;
 					}
-					dbg_slot += dbg_clock() - c1;
-					head = start + len;
-					// channel bytes: needed by the decoders from the start of the block
-					if (nq <= 8)
+					head = start + total;
+				}
+				dbg_slot += dbg_clock() - c1;
+				__syncwarp();
+				if (owner)
+				{
+					const uint32_t vs_l = m_vs, nq_l = m_vs >> 2;
+					BlockParams& P = Sl.P;
+					if (kRounds)
 					{
-						if (lane == j)
-							*reinterpret_cast<uint2*>(S.channels) = make_uint2(m_ch_lo, m_ch_hi);
+						P.round_members = lane == j ? cnt : 0u;
+						P.chain = (lane == j && chained) ? 1u : 0u;
 					}
-					else
-						for (uint32_t q = lane; q < nq; q += 32)
-							S.channels[q] = version ? __ldg(tail + vs + q) : (uint8_t)0;
-					__syncwarp();
-					if (lane == j)
+					if (m_valid)
 					{
-						ring_start[slot] = start;
-						ring_len[slot] = len;
-						BlockParams& P = S.P;
+						const uint32_t rows_bytes = vs_l <= kRowsInRingMaxVs ? 32u * vs_l : 0u;
+						const uint32_t at = start + before;
+						// channel bytes: needed by the decoders from the start of the block
+						if (nq_l <= 8)
+							*reinterpret_cast<uint2*>(Sl.channels) = make_uint2(m_ch_lo, m_ch_hi);
+						else
+						{
+							const uint8_t* ch = reinterpret_cast<const uint8_t*>(m_tail) + vs_l;
+							for (uint32_t q = 0; q < nq_l; ++q)
+								Sl.channels[q] = m_version ? __ldg(ch + q) : (uint8_t)0;
+						}
+						ring_start[slot_l] = at;
+						ring_len[slot_l] = m_len;
 						const uint32_t groups = (m_n + kGroup - 1) / kGroup;
 						const uint32_t gshift = groups > 8 ? 4u : (groups > 4 ? 3u : (groups > 2 ? 2u : (groups > 1 ? 1u : 0u)));
 						P.valid = 1;
-						P.vs = vs;
+						P.vs = vs_l;
 						P.n = m_n;
 						P.groups = groups;
 						P.gshift = gshift;
-						P.items = nq << gshift;
-						P.stage_off = start + m_shift;
-						P.rows_off = rows_bytes ? start + enc_bytes : kRowsInGlobal;
-						P.first = b == 0;
+						P.items = nq_l << gshift;
+						P.stage_off = at + m_shift;
+						P.rows_off = rows_bytes ? at + m_enc : kRowsInGlobal;
+						P.first = m_b == 0;
 						P.filter = m_filter;
-						P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs == 4) ? 1u : 2u);
-						P.m_chunk = magic_for(16 * vs);
+						P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs_l == 4) ? 1u : 2u);
+						P.m_chunk = magic_for(16 * vs_l);
 						P.out = reinterpret_cast<uint8_t*>(m_out);
 						P.rows_global = reinterpret_cast<const uint16_t*>(m_rows);
 						P.lookback = reinterpret_cast<unsigned long long*>(m_look);
-						if (kRounds)
-							P.round_members = round_members;
 
 						fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
-						mbar_expect_tx(full + slot, len);
-						tma_load_bulk(ring + start, reinterpret_cast<const void*>(m_lo), enc_bytes, full + slot);
+						mbar_expect_tx(full + slot_l, m_len);
+						tma_load_bulk(ring + at, reinterpret_cast<const void*>(m_lo), m_enc, full + slot_l);
 						if (rows_bytes)
-							tma_load_bulk(ring + start + enc_bytes, P.rows_global, rows_bytes, full + slot);
+							tma_load_bulk(ring + at + m_enc, P.rows_global, rows_bytes, full + slot_l);
 					}
-					__syncwarp();
-				}
-				else
-				{
-					dbg_slot += dbg_clock() - c1;
-					__syncwarp();
-					if (lane == j)
+					else
 					{
-						ring_len[slot] = 0;
-						S.P.valid = 0;
-						if (kRounds)
-							S.P.round_members = round_members;
-						mbar_arrive(full + slot);
+						ring_len[slot_l] = 0;
+						P.valid = 0;
+						mbar_arrive(full + slot_l);
+						if (kBlock)
+						{
+							// block mode: later blocks of the stream may still be decodable (their output is garbage, as the
+							// reference allows for a rejected stream) and must not wait for this block's look-back entries
+							unsigned long long* look = reinterpret_cast<unsigned long long*>(m_look);
+							for (uint32_t q = 0; q < nq_l; ++q)
+								st_volatile_u64(look + q, ((unsigned long long)((T.epoch << 2) | 2u)) << 32);
+						}
 					}
-					if (kBlock)
-					{
-						// block mode: later blocks of the stream may still be decodable (their output is garbage, as the
-						// reference allows for a rejected stream) and must not wait for this block's look-back entries
-						unsigned long long* look = reinterpret_cast<unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
-						for (uint32_t q = lane; q < nq; q += 32)
-							st_volatile_u64(look + q, ((unsigned long long)((T.epoch << 2) | 2u)) << 32);
-					}
-					__syncwarp();
 				}
+				__syncwarp();
+				g += cnt - 1; // (rounds form: the pass covered the whole round)
 
+				MOB200_TRACE_EVENT(T, unit, lane, 4, i);
 			} // do_stage
 
 			// ---- carry into the block, per 4-byte lane ---------------------------------------------------------------
 			if (do_carry)
 			{
 				const long long c2 = dbg_clock();
+				MOB200_TRACE_EVENT(T, unit, lane, 5, i);
 				bool carry_done = false;
 				if (valid && b > 0 && nq <= 8)
 				{
@@ -639,8 +757,17 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				}
 				// every lane releases its own carry words (the barrier counts the 32 producer lanes)
 				mbar_arrive(carry_bar + slot);
+				if (kRounds && chained)
+				{
+					// chained round: the decoder warps hand the carry on from member to member; the other members' barriers
+					// only have to complete their phase
+					for (uint32_t k = 1; k < members; ++k)
+						mbar_arrive(carry_bar + ((i + k) & (kSlots - 1)));
+					g = members - 1;
+				}
 				__syncwarp();
 				dbg_look += dbg_clock() - c2;
+				MOB200_TRACE_EVENT(T, unit, lane, 6, i);
 			} // do_carry
 
 			if (!kRounds)
@@ -652,10 +779,21 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			}
 			else if (++g == members)
 			{
-				g = 0;
-				if (pass == 1)
-					j0 += members;
-				pass ^= 1u;
+				if (mode == 1)
+				{
+					sj += n_members;
+					if (a_have)
+						n_wait = true, mode = 2, g = 0; // N is staged: now the carries of A
+					else
+						a_j0 = n_j0, a_members = n_members, a_chained = n_chained, a_have = true, mode = 0;
+				}
+				else
+				{
+					a_have = false;
+					if (n_wait)
+						a_j0 = n_j0, a_members = n_members, a_chained = n_chained, a_have = true, n_wait = false;
+					mode = 0;
+				}
 			}
 		}
 	}
@@ -830,12 +968,19 @@ struct DecoderCtx
 	uint64_t* tile_free;
 	unsigned long long tag;
 	uint32_t lane;
+	const DevTables* T; // (event trace)
+	uint32_t unit, warp, index;
 };
 
 // One work quantum: 32 items of one block (item = 4 byte-channels x 16 vertices): unpack, transposes, deltas and scans
 // in registers, finished words into the block's part of the output tile.
+// kChain (rounds form): the quantum belongs to member `chain_g` of a chained round whose first member sits in slot S0
+// (carry_slot / phase are that member's): the members' aggregates meet in shared memory, one barrier of the decoder
+// warps later every member knows the value in front of it without a look-back through global memory.
+template <bool kChain>
 __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotData& S, const BlockRegs& B, uint8_t* tile, uint64_t* carry_slot, uint32_t phase,
-    uint32_t base, bool first_of_block, uint32_t tile_uses, long long& dbg_carry, long long& dbg_tile)
+    uint32_t base, bool first_of_block, uint32_t tile_uses, long long& dbg_carry, long long& dbg_tile, SlotData* slots = nullptr, uint32_t slot0 = 0, uint32_t slot_mask = 0,
+    uint32_t chain_g = 0, uint32_t bar_id = 0)
 {
 	uint8_t* ring = X.ring;
 	const uint32_t* patch_lut = X.patch_lut;
@@ -993,10 +1138,19 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 	if (last && !first_block)
 		st_volatile_u64(lookback + q, tag | (1ull << 32) | incl); // state 1: aggregate of this block
 
+	if (kChain)
+	{
+		if (last)
+			slots[(slot0 + chain_g) & slot_mask].chain_total[q] = incl;
+		decoder_sync(bar_id); // all four decoder warps (a warp without a quantum in this round joins in decoder_main)
+	}
+
 	if (first_of_block)
 	{
 		const long long c0 = dbg_clock();
+		MOB200_TRACE_EVENT(*X.T, X.unit, lane, 32 + X.warp * 8 + 2, X.index);
 		mbar_wait(carry_slot, phase);
+		MOB200_TRACE_EVENT(*X.T, X.unit, lane, 32 + X.warp * 8 + 3, X.index);
 		const long long c1 = dbg_clock();
 		mbar_wait(tile_free, (tile_uses & 1u) ^ 1u); // every warp has finished storing the previous tile
 		dbg_carry += c1 - c0;
@@ -1005,7 +1159,10 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 
 	if (active)
 	{
-		const uint32_t carry = S.carry[q];
+		uint32_t carry = kChain ? slots[slot0 & slot_mask].carry[q] : S.carry[q];
+		if (kChain)
+			for (uint32_t h = 0; h < chain_g; ++h)
+				carry = lane_combine(carry, slots[(slot0 + h) & slot_mask].chain_total[q], H);
 		if (last)
 			st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
 		uint32_t v = lane_combine(carry, excl, H);
@@ -1153,10 +1310,11 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 	X.tile_free = tile_free;
 	X.tag = (unsigned long long)(T.epoch << 2) << 32;
 	X.lane = lane;
+	X.T = &T, X.unit = unit, X.warp = tid >> 5, X.index = 0;
 	uint32_t tile_uses = 0;
 	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
 	const long long dbg_t0 = dbg_clock();
-	const uint32_t my_count = unit < T.total_blocks ? (T.total_blocks - unit + T.units - 1) / T.units : 0u;
+	const uint32_t my_count = unit_block_count(T, unit);
 
 	// Rounds variant: one ROUND = consecutive blocks of this unit's sequence whose work fits the four decoder warps: a
 	// work quantum is 32 items (one warp), a block has ceil(items / 32) of them.  Blocks of small vertices (4 ... 16
@@ -1168,6 +1326,8 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 		const uint32_t slot = i & (kSlots - 1);
 		const uint32_t phase = (i / kSlots) & 1u;
 		const SlotData& S = slots[slot];
+		X.index = i;
+		MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 0, i);
 		{
 			const long long c0 = dbg_clock();
 			mbar_wait(full + slot, phase);
@@ -1186,7 +1346,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			}
 			const BlockRegs B = load_block(S);
 			for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
-				decode_quantum(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
+				decode_quantum<false>(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
 			++tile_uses;
 
 			// this warp no longer needs the slot (staging bytes, rows, params, carry)
@@ -1230,7 +1390,14 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 				}
 			}
 			const uint32_t warp = tid >> 5;
-			if (warp < quanta)
+			const bool chained = S.P.chain != 0;
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 1, i);
+			if (warp >= quanta)
+			{
+				if (chained)
+					decoder_sync(bar_id); // the barrier inside the chained decode_quantum
+			}
+			else
 			{
 				// the member this warp's quantum belongs to
 				uint32_t g = 0, qb = 0;
@@ -1242,11 +1409,16 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 				const uint32_t sg = (i + g) & (kSlots - 1);
 				const SlotData& Sg = slots[sg];
 				const BlockRegs B = load_block(Sg);
-				decode_quantum(X, Sg, B, btile, carry_bar + sg, ((i + g) / kSlots) & 1u, (warp - qb) * 32u, true, tile_uses, dbg_carry, dbg_tile);
+				if (chained)
+					decode_quantum<true>(X, Sg, B, btile, carry_bar + slot, phase, (warp - qb) * 32u, true, tile_uses, dbg_carry, dbg_tile, slots, i, kSlots - 1, g, bar_id);
+				else
+					decode_quantum<false>(X, Sg, B, btile, carry_bar + sg, ((i + g) / kSlots) & 1u, (warp - qb) * 32u, true, tile_uses, dbg_carry, dbg_tile);
 			}
 			++tile_uses;
 
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 4, i);
 			decoder_sync(bar_id); // the tiles of the round are complete
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 5, i);
 
 #pragma unroll 1
 			for (uint32_t g = 0; g < members; ++g)
@@ -1264,6 +1436,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 				if (g < members)
 					release_slot<true>(empty + ((i + g) & (kSlots - 1)), lane);
 			mbar_arrive(tile_free);
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 6, i);
 			i += members;
 		}
 	}

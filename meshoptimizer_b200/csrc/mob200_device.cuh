@@ -21,6 +21,29 @@ __device__ __forceinline__ long long dbg_clock()
 #endif
 }
 
+// Event trace of one decode unit (diagnostics; only in a library built with -DMOB200_TRACE, tools/trace_unit.py): the
+// producer lane 0 and lane 0 of every decoder warp append (globaltimer ns << 16 | event << 8 | block index & 255).
+#ifdef MOB200_TRACE
+#ifndef MOB200_TRACE_UNIT
+#define MOB200_TRACE_UNIT 300
+#endif
+constexpr uint32_t kTraceWords = 16384; // u64 entries behind the counters; entry 0 = number of events
+__device__ __forceinline__ void trace_event(const DevTables& T, uint32_t unit, uint32_t lane, uint32_t ev, uint32_t i)
+{
+	if (unit != MOB200_TRACE_UNIT || lane != 0)
+		return;
+	unsigned long long* tr = reinterpret_cast<unsigned long long*>(T.counters + 64);
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	const unsigned long long k = atomicAdd(tr, 1ull) + 1ull;
+	if (k < kTraceWords)
+		tr[k] = (t << 16) | ((unsigned long long)(ev & 255u) << 8) | (i & 255u);
+}
+#define MOB200_TRACE_EVENT(T, unit, lane, ev, i) trace_event(T, unit, lane, ev, i)
+#else
+#define MOB200_TRACE_EVENT(T, unit, lane, ev, i) ((void)0)
+#endif
+
 __device__ __forceinline__ uint32_t smem_addr(const void* p)
 {
 	return (uint32_t)__cvta_generic_to_shared(p);

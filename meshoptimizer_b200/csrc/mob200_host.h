@@ -101,6 +101,7 @@ struct mob200_Context
 	uint32_t walker_lead = 0;      // see DevTables::walker_lead
 	int rounds_mode = 2;           // 0 / 1 force the decoder form, 2 = rounds when most blocks have <= 16-byte vertices (MOB200_ROUNDS)
 	int wide_walk_mode = 2;        // 0 / 1 force the walker form, 2 = choose by stream count (MOB200_WIDE_WALK)
+	int run_major = 1;             // block mode + rounds: decode order in runs of four consecutive blocks of a stream (MOB200_RUN_MAJOR=0: level-major)
 	int team_walk = 1;             // few-stream plans: offsets-only team walk + block-mode decode (two launches) instead of the fused
 	                               // one-warp-per-stream walker (MOB200_TEAM_WALK=0 restores that)
 	cudaStream_t stream = nullptr; // used by the host-pointer entry points

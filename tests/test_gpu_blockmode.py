@@ -202,3 +202,73 @@ def test_segmenter_streams_and_sidecars_decode_on_the_device(mb, vs, total, seg,
     outs, status, plan, guard = device_run(w, runs=0, sidecars=sidecars, block_runs=1)
     assert (status == 0).all() and guard
     assert np.array_equal(np.concatenate(outs), v)
+
+
+# ---- block mode + rounds form: run-major decode order, carries chained inside a round by the decoder warps ---------------
+
+@pytest.fixture
+def rounds_ctx(mb, monkeypatch):
+    """a context with the rounds form forced on (the heuristic wants >= 8 blocks per decode unit)"""
+    monkeypatch.setenv("MOB200_ROUNDS", "1")
+    ctx = mb.Context(-1)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("kind,count,seg,version,level", [
+    ("oct8", 800_000, None, 1, 2),       # one stream, 3125 four-byte blocks: every round is a run of four blocks of it
+    ("quat12", 800_003, None, 1, 2),     # 8-byte vertices, ragged last block
+    ("exp15", 900_000, None, 1, 2),      # 12-byte vertices: two quanta per block, runs of two
+    ("color12", 2_560_000, 2560, 1, 2),  # 1000 streams x 10 blocks: the last run of a stream has two blocks, rounds straddle streams
+    ("oct8", 1_000_000, 700, 1, 2),      # 1429 streams of three blocks (no full run at all)
+    ("oct8", 1 << 22, 1 << 12, 0, 0),    # 1024 streams x 16 blocks, codec v0
+    ("exp16", 1 << 21, 1 << 11, 1, 3),   # 1024 streams x 8 blocks, level 3 (xor / 16-bit channels)
+    ("color8", 300_000, 257, 1, 2),      # streams of two blocks, the second nearly empty
+])
+def test_block_mode_rounds_run_major(mb, rounds_ctx, kind, count, seg, version, level):
+    w = workloads.c3(kind, count=count, seg=seg, version=version, level=level)
+    want = _expected(w)
+    outs, status, plan, guard = device_run(w, ctx=rounds_ctx, runs=0, sidecars=_sidecars(w), block_runs=3)
+    assert (status == 0).all() and guard
+    assert _same(w, outs, want) is None, _same(w, outs, want)
+
+
+def test_block_mode_rounds_mixed_sizes_and_bad_blocks(mb, rounds_ctx):
+    """4- ... 32-byte vertices in one plan (runs of four, rounds of one / two / four members), one stream with a stale
+    sidecar entry in the middle of a run and one with a framing error: the others decode bit-exact"""
+    parts = [workloads.c3("oct8", count=300_000, seg=1500), workloads.c3("quat12", count=200_000, seg=999),
+             workloads.c3("exp16", count=150_000, seg=4000), workloads.c1b(version=1, count=200_000),
+             workloads.c2(total=1 << 17, seg=3000, level=2, version=1), workloads.c3("color8", count=100_000, seg=257, version=0, level=0)]
+    w = workloads.merge("mixed", parts)
+    want = _expected(w)
+    sc = _sidecars(w)
+    bad = [s.copy() for s in sc]
+    i_stale = next(i for i in range(w.n) if int(w.vertex_sizes[i]) == 4 and int(w.counts[i]) > 4 * 256)
+    i_magic = next(i for i in range(w.n) if int(w.vertex_sizes[i]) == 8)
+    bad[i_stale][2] += 1                # a four-byte stream of six blocks: block 2 (inside the first run) starts one byte late
+    blob = w.blob.copy()
+    blob[int(w.offsets[i_magic])] = 0x55  # bad magic
+    outs, status, plan, guard = device_run(w, ctx=rounds_ctx, runs=0, sidecars=bad, block_runs=2, blob_override=blob)
+    assert guard
+    assert status[i_stale] == mb.ERR_SIDECAR and status[i_magic] == -1
+    ok = [i for i in range(w.n) if i not in (i_stale, i_magic)]
+    assert (status[ok] == 0).all()
+    for i in ok:
+        if int(w.vertex_sizes[i]) == 4 and int(w.filters[i]) in (1, 4):
+            d = np.abs(outs[i].astype(np.int16) - want[i].astype(np.int16))
+            assert int(np.minimum(d, 256 - d).max(initial=0)) <= 1, i
+        else:
+            assert np.array_equal(outs[i], want[i]), i
+
+
+def test_block_mode_rounds_level_major_still_available(mb, monkeypatch):
+    """MOB200_RUN_MAJOR=0 keeps the level-major order (diagnostics / comparison runs)"""
+    monkeypatch.setenv("MOB200_ROUNDS", "1")
+    monkeypatch.setenv("MOB200_RUN_MAJOR", "0")
+    ctx = mb.Context(-1)
+    try:
+        w = workloads.c3("quat12", count=400_000, seg=5000)
+        outs, status, plan, guard = device_run(w, ctx=ctx, runs=0, sidecars=_sidecars(w), block_runs=2)
+        assert (status == 0).all() and guard and _same(w, outs, _expected(w)) is None
+    finally:
+        ctx.close()
