@@ -88,6 +88,7 @@ typedef struct mob200_Plan mob200_Plan;       /* a prepared batch: descriptors +
 
 /* device < 0 selects the current CUDA device.  Returns 0 or MOB200_ERR_CUDA. */
 MESHOPTIMIZER_API int mob200_context_create(mob200_Context** out, int device);
+/* A plan points at its context: destroy the plans of a context before the context. */
 MESHOPTIMIZER_API void mob200_context_destroy(mob200_Context* ctx);
 
 /* Prepare a batch of n streams whose src/dst are device pointers: uploads the descriptor table and

@@ -16,6 +16,7 @@ There is NO CPU fallback: every entry point goes through the CUDA library and ra
 from __future__ import annotations
 
 import ctypes
+import weakref
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_void_p
 from typing import Iterable, Optional, Sequence
@@ -339,6 +340,9 @@ class Context:
 
     def close(self) -> None:
         if self.handle:
+            # plans point at their context (include/meshopt_b200.h: destroy a context's plans first)
+            for p in list(getattr(self, "_plans", ())):
+                p.close()
             lib().mob200_context_destroy(self.handle)
             self.handle = None
 
@@ -397,6 +401,9 @@ class Plan:
         if rc != 0:
             raise RuntimeError(f"mob200_plan_create failed ({rc})")
         self.handle = h
+        if not hasattr(ctx, "_plans"):
+            ctx._plans = weakref.WeakSet()
+        ctx._plans.add(self)
 
     def run(self, cuda_stream: int = 0, block_parallel: bool = False) -> None:
         rc = lib().mob200_plan_run_ex(self.handle, c_void_p(cuda_stream), RUN_BLOCK_PARALLEL if block_parallel else 0)

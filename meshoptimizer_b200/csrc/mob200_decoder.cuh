@@ -1427,7 +1427,8 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 				if (!Sg.P.valid)
 					continue;
 				const BlockRegs B = load_block(Sg);
-				store_block(B, tile + (g == 0 ? moff[0] : (g == 1 ? moff[1] : (g == 2 ? moff[2] : moff[3]))), tid, bar_id);
+				// (member g starts at warp g: a block of 4-byte vertices has 64 sixteen-byte pieces, two warps' worth)
+				store_block(B, tile + (g == 0 ? moff[0] : (g == 1 ? moff[1] : (g == 2 ? moff[2] : moff[3]))), (tid + g * 32u) & (kDecodeThreads - 1), bar_id);
 			}
 			// the slots are released after the stores: the store parameters of the members are read from them (with eight
 			// slots the producer still stages the whole next round meanwhile)
