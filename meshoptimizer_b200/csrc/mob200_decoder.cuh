@@ -253,6 +253,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		const bool has = lane < kProducerBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0, m_ready = 0;
 		uint32_t m_s = 0xffffffffu; // stream of the block (chained rounds)
+		uint32_t m_magic = 0;       // ceil(2^32 / (16 * vertex size)): a division, done here for all blocks of the batch at once
 		uint32_t m_quanta = 0, m_len = 0; // rounds variant: decoder work quanta (32 items each) and staged bytes of the block
 		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
 		const uint32_t* boff = nullptr;
@@ -269,6 +270,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			src_size = d->src_size;
 			const uint32_t vs = d->vertex_size;
 			m_vs = vs;
+			m_magic = magic_for(16 * vs);
 			m_b = b;
 			m_filter = d->filter;
 			const uint32_t bv = d->block_groups * kGroup;
@@ -475,7 +477,6 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			const uint32_t members = mode == 1 ? n_members : a_members;
 			const bool chained = mode == 1 ? n_chained : a_chained;
 			const uint32_t j = kRounds ? (mode == 1 ? n_j0 : a_j0) + g : (plain_stage ? js : jc);
-			const uint32_t round_members = g == 0 ? members : 0u;
 			const bool do_stage = kRounds ? mode == 1 : plain_stage, do_carry = kRounds ? mode == 2 : !plain_stage;
 			const uint32_t i = i0 + j;
 			const uint32_t slot = i & (kSlots - 1);
@@ -483,9 +484,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			const bool valid = __shfl_sync(0xffffffffu, m_valid, j) != 0;
 			const uint32_t vs = __shfl_sync(0xffffffffu, m_vs, j);
 			const uint32_t nq = vs >> 2;
-			const uint32_t version = __shfl_sync(0xffffffffu, m_version, j);
 			const uint32_t b = __shfl_sync(0xffffffffu, m_b, j);
-			const uint8_t* tail = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, m_tail, j));
 
 			if (do_stage)
 			{
@@ -592,7 +591,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						P.first = m_b == 0;
 						P.filter = m_filter;
 						P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs_l == 4) ? 1u : 2u);
-						P.m_chunk = magic_for(16 * vs_l);
+						P.m_chunk = m_magic;
 						P.out = reinterpret_cast<uint8_t*>(m_out);
 						P.rows_global = reinterpret_cast<const uint16_t*>(m_rows);
 						P.lookback = reinterpret_cast<unsigned long long*>(m_look);
@@ -650,6 +649,17 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						if (q0 + 3 < nq)
 							S.carry[q0 + 3] = (uint32_t)pre3;
 					}
+				}
+				if (!kRounds && kBlock && valid && !carry_done && b > 0 && nq <= 32)
+				{
+					// (plain form; a round's predecessor is usually still in flight, the extra round trip measured 8 % slower there)
+					// the usual case when the predecessor lies a generation of blocks back: it has published its inclusive
+					// prefix -- one load per 4-byte lane, none of the look-back loop's instructions fetched
+					const unsigned long long* look1 = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
+					const unsigned long long e = lane < nq ? ld_volatile_u64(look1 + lane - nq) : 0ull;
+					carry_done = __all_sync(0xffffffffu, lane >= nq || (uint32_t)(e >> 32) == (((T.epoch & 0x3fffffffu) << 2) | 2u));
+					if (carry_done && lane < nq)
+						S.carry[lane] = (uint32_t)e;
 				}
 				if (kBlock && valid && !carry_done && b > 0 && nq <= 32)
 				{
@@ -724,6 +734,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				else if (valid && !carry_done)
 				{
 					const unsigned long long* look = reinterpret_cast<const unsigned long long*>(__shfl_sync(0xffffffffu, m_look, j));
+					const uint8_t* tail = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, m_tail, j));
 					for (uint32_t q = lane; q < nq; q += 32)
 					{
 						const uint32_t channel = S.channels[q];
