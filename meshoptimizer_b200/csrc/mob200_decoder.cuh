@@ -29,7 +29,11 @@ namespace mob200
 {
 
 constexpr uint32_t kRoundBlocks = 4;           // rounds variant: blocks the decoder warps of a unit take in one round (one warp per block)
-constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight
+#ifndef MOB200_PLAIN_RING
+#define MOB200_PLAIN_RING 14336
+#endif
+constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight (rounds form; the least any form needs)
+constexpr uint32_t kPlainRingBytes = MOB200_PLAIN_RING; // plain form: 16 KB measured the same, 18 KB 2 % slower (less of the SM's L1 left beside 230 KB of shared memory)
 constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
 constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
@@ -74,7 +78,8 @@ struct Lay
 	static constexpr uint32_t kSlots = kRounds ? 8 : 4; // blocks in flight between producer and decoders
 	static constexpr uint32_t kTileBytes = kBlockBytes + (kRounds ? kRoundBlocks : 1) * 16 * kTilePad; // one 8 KB block, or up to four smaller ones side by side
 	static constexpr uint32_t kSmemStage = 0;
-	static constexpr uint32_t kSmemTile = kSmemStage + kStageRingBytes;
+	static constexpr uint32_t kRing = kRounds ? kStageRingBytes : kPlainRingBytes;
+	static constexpr uint32_t kSmemTile = kSmemStage + kRing;
 	static constexpr uint32_t kSmemPatch = kSmemTile + kTileBytes;            // escape-byte selector table: 16 x 4 bytes
 	static constexpr uint32_t kSmemSlots = kSmemPatch + 64;
 	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
@@ -88,7 +93,7 @@ struct Lay
 constexpr uint32_t kSmemWalkerBytes = 32 * 512 + 6 * 4 * 32 + 16; // = kWalkSmemBytes (mob200_walker.cuh) >= kWideSmemBytes
 
 static_assert(sizeof(BlockParams) == 80 && sizeof(SlotData) == 416, "SlotData layout");
-static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs, "staging ring must hold the largest block");
+static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs && kPlainRingBytes >= kStageRingBytes && kPlainRingBytes % 16 == 0, "staging ring must hold the largest block");
 
 uint32_t decode_smem_bytes()
 {
@@ -386,7 +391,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				for (uint32_t u = jc; u < js && so == 0xffffffffu; ++u)
 					if (ring_len[(i0 + u) & (kSlots - 1)])
 						so = ring_start[(i0 + u) & (kSlots - 1)];
-				plain_stage = so == 0xffffffffu || (head > so ? (head + lens <= kStageRingBytes || lens < so) : head + lens < so);
+				plain_stage = so == 0xffffffffu || (head > so ? (head + lens <= L::kRing || lens < so) : head + lens < so);
 			}
 			if (kRounds && mode == 0)
 			{
@@ -406,7 +411,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						for (uint32_t k = 1; k < kRoundBlocks && open && j0 + k < in_batch; ++k)
 						{
 							const uint32_t qn = __shfl_sync(0xffffffffu, m_quanta, (j0 + k) & 31u), bn = __shfl_sync(0xffffffffu, m_len, (j0 + k) & 31u);
-							if (qs + qn <= kDecodeThreads / 32 && bs + bn <= kStageRingBytes / 2)
+							if (qs + qn <= kDecodeThreads / 32 && bs + bn <= L::kRing / 2)
 							{
 								qs += qn, bs += bn;
 								members = k + 1;
@@ -454,7 +459,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 								continue;
 							if (h > so)
 							{
-								if (h + len <= kStageRingBytes)
+								if (h + len <= L::kRing)
 									h += len;
 								else if (len < so)
 									h = len;
@@ -531,7 +536,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						const uint32_t so = ring_start[f & (kSlots - 1)];
 						if (head > so)
 						{
-							if (head + total <= kStageRingBytes)
+							if (head + total <= L::kRing)
 							{
 								start = head;
 								break;
