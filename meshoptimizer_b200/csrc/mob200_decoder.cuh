@@ -33,7 +33,7 @@ constexpr uint32_t kRoundBlocks = 4;           // rounds variant: blocks the dec
 #define MOB200_PLAIN_RING 14336
 #endif
 constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + group-table rows of the blocks in flight (rounds form; the least any form needs)
-constexpr uint32_t kPlainRingBytes = MOB200_PLAIN_RING; // plain form: 16 KB measured the same, 18 KB 2 % slower (less of the SM's L1 left beside 230 KB of shared memory)
+constexpr uint32_t kPlainRingBytes = MOB200_PLAIN_RING; // plain form: 16 KB measured the same, 18 KB 2 % slower
 constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
 constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
