@@ -186,7 +186,12 @@ constexpr uint32_t kCarryLag = MOB200_CARRY_LAG; // block mode: blocks the produ
 #define MOB200_ROUND_LAG 0
 #endif
 constexpr uint32_t kRoundLag = MOB200_ROUND_LAG; // rounds form, block mode: rounds staged ahead of the oldest unresolved carry (0 or 1)
+#ifndef MOB200_BLOCK_BATCH
+#define MOB200_BLOCK_BATCH 32
+#endif
 constexpr uint32_t kProducerBatch = 16;// blocks whose metadata chains (ticket -> stream -> progress -> offsets) are in flight together, one per lane
+constexpr uint32_t kProducerBatchBlock = MOB200_BLOCK_BATCH; // ... in block mode: the walkers are far ahead, a larger batch halves the pauses between batches
+constexpr uint32_t kPrefetchBlocks = 16; // blocks of a batch whose predecessor's look-back entries are prefetched (two lanes each)
 static_assert(kRoundBlocks == (1u << kRunShiftMax) && kProducerBatch % kRoundBlocks == 0, "a ticket chunk (one run of a stream) must not straddle two metadata batches");
 
 // debug counters (cycles, summed over CTAs): see mob200_plan_debug_counters
@@ -246,7 +251,9 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 	long long dbg_meta = 0, dbg_slot = 0, dbg_look = 0;
 	const long long dbg_t0 = dbg_clock();
 
-	for (uint32_t i0 = 0; i0 < my_count; i0 += kProducerBatch)
+	constexpr uint32_t kBatch = kBlock ? kProducerBatchBlock : kProducerBatch;
+	static_assert(kBatch <= 32 && kBatch % kRoundBlocks == 0, "one lane per block of a batch");
+	for (uint32_t i0 = 0; i0 < my_count; i0 += kBatch)
 	{
 		// ---- metadata of up to kProducerBatch blocks, one per lane: the dependent global loads of all of them overlap ----
 		const long long c0 = dbg_clock();
@@ -255,7 +262,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		// version); level 3: block byte range, channel bytes, and -- four entries per lane, two lanes per block -- the
 		// look-back entries of the predecessor block.  Everything of one level is requested before any of it is used.
 		const uint32_t mi = i0 + lane;
-		const bool has = lane < kProducerBatch && mi < my_count;
+		const bool has = lane < kBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0, m_ready = 0;
 		uint32_t m_s = 0xffffffffu; // stream of the block (chained rounds)
 		uint32_t m_magic = 0;       // ceil(2^32 / (16 * vertex size)): a division, done here for all blocks of the batch at once
@@ -361,7 +368,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		MOB200_TRACE_EVENT(T, unit, lane, 2, i0);
 
 		// ---- hand the blocks to the decoders, in order -------------------------------------------------------------
-		const uint32_t in_batch = min(kProducerBatch, my_count - i0);
+		const uint32_t in_batch = min(kBatch, my_count - i0);
 		// Rounds variant: the members of a round are all staged (slot, ring piece, TMA) before the carry of any of them is
 		// resolved -- the decoders start a round when every member has landed, and a carry may depend on a block that
 		// another unit decodes in a round of the same age, so a copy that waited for a carry could close a cycle.
@@ -634,7 +641,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				const long long c2 = dbg_clock();
 				MOB200_TRACE_EVENT(T, unit, lane, 5, i);
 				bool carry_done = false;
-				if (valid && b > 0 && nq <= 8)
+				if (valid && b > 0 && nq <= 8 && j < kPrefetchBlocks)
 				{
 					// the prefetched look-back entries: good if every one of them is an inclusive prefix of this run
 					const bool mine = (lane >> 1) == j;
