@@ -20,12 +20,24 @@ SLOTS = 8     # Lay<true>::kSlots
 BATCH = 16    # kProducerBatch
 
 
-def finishes(n_streams: int, blocks_per_stream: int, units: int, stage_first: bool) -> bool:
+def finishes(n_streams: int, blocks_per_stream: int, units: int, stage_first: bool, run_major: bool = False) -> bool:
     total = n_streams * blocks_per_stream
     units = min(units, total)
-    # level-major decode order: ticket t = block (t // n_streams) of stream (t % n_streams); unit u takes u, u + units, ...
-    queue = {u: list(range(u, total, units)) for u in range(units)}
-    pred = {t: (t - n_streams if t >= n_streams else None) for t in range(total)}
+    if not run_major:
+        # level-major decode order: ticket t = block (t // n_streams) of stream (t % n_streams); unit u takes u, u + units, ...
+        queue = {u: list(range(u, total, units)) for u in range(units)}
+        pred = {t: (t - n_streams if t >= n_streams else None) for t in range(total)}
+        block_of = {t: (t % n_streams, t // n_streams) for t in range(total)}
+    else:
+        # block mode + rounds (section 5.6): runs of ROUND consecutive blocks of a stream, level-major over the runs; the
+        # order is dealt to the units in chunks of ROUND tickets (chunk c -> unit c % units)
+        order = [(s, b) for b0 in range(0, blocks_per_stream, ROUND) for s in range(n_streams) for b in range(b0, min(b0 + ROUND, blocks_per_stream))]
+        ticket = {sb: t for t, sb in enumerate(order)}
+        block_of = dict(enumerate(order))
+        pred = {t: (ticket[(s, b - 1)] if b else None) for t, (s, b) in block_of.items()}
+        chunks = [list(range(c, min(c + ROUND, total))) for c in range(0, total, ROUND)]
+        units = min(units, len(chunks))
+        queue = {u: [t for c in chunks[u::units] for t in c] for u in range(units)}
     # rounds: consecutive members of a queue, never across a producer batch
     rounds = {}   # ticket -> (unit, round index, position in round, members of the round)
     unit_rounds = {}
@@ -61,7 +73,13 @@ def finishes(n_streams: int, blocks_per_stream: int, units: int, stage_first: bo
                 ok = ok and all(m in done for m in prev_round)                     # ... after finishing the previous round
                 if ok:
                     unpacked.add(t); progress = True
-            if t not in carried:
+            chained = run_major and len(members) > 1 and all(
+                block_of[m][0] == block_of[members[0]][0] and block_of[m][1] == block_of[members[0]][1] + k for k, m in enumerate(members))
+            if t not in carried and chained and pos > 0:
+                # chained round: the decoder warps hand the first member's carry on through the members' aggregates
+                if members[0] in carried and all(m in unpacked for m in members[:pos]):
+                    carried.add(t); progress = True
+            elif t not in carried:
                 ok = t in staged and all(m in carried for m in members[:pos])
                 if stage_first:
                     ok = ok and all(m in staged for m in members)
@@ -95,3 +113,11 @@ def test_carry_after_each_copy_can_deadlock():
     """the schedule of the first version: one long stream, more than two rounds per unit"""
     assert not finishes(1, 64, 5, stage_first=False)
     assert not finishes(7, 12, 5, stage_first=False)
+
+
+def test_run_major_chained_rounds_finish():
+    """block mode + rounds: run-major order, carries chained inside a round by the decoder warps"""
+    for n_streams, blocks, units in CASES + [(1, 7, 3), (3, 6, 2), (5, 3, 4), (2, 17, 16)]:
+        assert finishes(n_streams, blocks, units, stage_first=True, run_major=True), (n_streams, blocks, units)
+    for n_streams, blocks, units in itertools.product(range(1, 7), (1, 2, 5, 9, 17), (1, 2, 3, 5, 8)):
+        assert finishes(n_streams, blocks, units, stage_first=True, run_major=True), (n_streams, blocks, units)
