@@ -1017,6 +1017,10 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 	const uint32_t gstride = 1u << gshift;
 
 	const uint32_t item = base + lane;
+	// item -> (4-byte lane q, chunk c): consecutive items share a lane, a warp takes two NEIGHBOURING lanes of a 32-byte
+	// vertex.  (Neighbours are of one kind and take the same unpack paths.  The unit trace shows the price -- unpack 2.2 /
+	// 1.8 / 2.4 / 2.7 us per warp on C2b, the block's barrier waits for the slowest -- but pairing lane k with lane
+	// k + nq/2 to even the warps out measured 7 % SLOWER: two kinds of lanes in a warp run both kinds' paths.)
 	const uint32_t q = item >> gshift;
 	const uint32_t c = item & (gstride - 1u);
 	const bool active = item < items && c < groups;
@@ -1360,6 +1364,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 
 		if (members <= 1)
 		{
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 1, i);
 			// ---- one block: its quanta go round the four warps ---------------------------------------------------------
 			++i;
 			if (!S.P.valid)
@@ -1375,12 +1380,15 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			// this warp no longer needs the slot (staging bytes, rows, params, carry)
 			release_slot<kRounds>(empty + slot, lane);
 
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 4, i - 1);
 			decoder_sync(bar_id); // the tile is complete
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 5, i - 1);
 			store_block(B, tile, tid, bar_id);
 			// every thread arrives for its own reads of the tile (an elected lane's arrival after __syncwarp is just as
 			// ordered under the PTX memory model and measured the same, but compute-sanitizer's racecheck credits an
 			// arrival only to the arriving thread)
 			mbar_arrive(tile_free);
+			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 6, i - 1);
 			continue;
 		}
 
