@@ -1395,7 +1395,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 		if (kRounds)
 		{
 			// ---- a round of several small blocks: one quantum per warp, every block in its own part of the tile ----------
-			uint32_t quanta = 0, tile_used = 0;
+			uint32_t quanta = 0, tile_used = 0, round_n = 0;
 			uint32_t mq[kRoundBlocks], moff[kRoundBlocks];
 #pragma unroll
 			for (uint32_t g = 0; g < kRoundBlocks; ++g)
@@ -1417,6 +1417,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 						moff[g] = tile_used;
 						tile_used += tile_span(Sg.P.groups, Sg.P.vs);
 						quanta += mq[g];
+						round_n += Sg.P.n;
 					}
 				}
 			}
@@ -1451,13 +1452,18 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			decoder_sync(bar_id); // the tiles of the round are complete
 			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 5, i);
 
+			// a chained round is one piece of output: consecutive blocks of one stream, every member but the last 256 vertices
+			// (16 chunks), so the members' outputs AND their parts of the tile follow each other -- one store pass
+			const uint32_t stores = chained ? 1u : members;
 #pragma unroll 1
-			for (uint32_t g = 0; g < members; ++g)
+			for (uint32_t g = 0; g < stores; ++g)
 			{
 				const SlotData& Sg = slots[(i + g) & (kSlots - 1)];
 				if (!Sg.P.valid)
 					continue;
-				const BlockRegs B = load_block(Sg);
+				BlockRegs B = load_block(Sg);
+				if (chained)
+					B.n = round_n;
 				// (member g starts at warp g: a block of 4-byte vertices has 64 sixteen-byte pieces, two warps' worth)
 				store_block(B, tile + (g == 0 ? moff[0] : (g == 1 ? moff[1] : (g == 2 ? moff[2] : moff[3]))), (tid + g * 32u) & (kDecodeThreads - 1), bar_id);
 			}
