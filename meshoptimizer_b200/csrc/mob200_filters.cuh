@@ -184,4 +184,31 @@ __device__ __noinline__ uint2 apply_filter64(uint2 v, int filter)
 	}
 }
 
+// a 16-byte piece at a time: the four (two) independent elements are interleaved by the compiler inside ONE call -- as
+// single-element calls the decoders' store pass ran them back to back, each a dependent chain with a division and a
+// square root (unit trace, 4-byte normals: 3.1 us of a round's 8 us)
+__device__ __noinline__ uint4 apply_filter32x4(uint4 v, int filter)
+{
+	switch (filter)
+	{
+	case 1: return make_uint4(filter_oct8(v.x), filter_oct8(v.y), filter_oct8(v.z), filter_oct8(v.w));
+	case 3: return make_uint4(filter_exp(v.x), filter_exp(v.y), filter_exp(v.z), filter_exp(v.w));
+	case 4: return make_uint4(filter_color8(v.x), filter_color8(v.y), filter_color8(v.z), filter_color8(v.w));
+	default: return v;
+	}
+}
+
+__device__ __noinline__ uint4 apply_filter64x2(uint4 v, int filter)
+{
+	uint2 a = make_uint2(v.x, v.y), b = make_uint2(v.z, v.w);
+	switch (filter)
+	{
+	case 1: a = filter_oct16(a), b = filter_oct16(b); break;
+	case 2: a = filter_quat(a), b = filter_quat(b); break;
+	case 4: a = filter_color16(a), b = filter_color16(b); break;
+	default: break;
+	}
+	return make_uint4(a.x, a.y, b.x, b.y);
+}
+
 } // namespace mob200
