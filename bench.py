@@ -334,6 +334,7 @@ class DeviceWorkload:
         assert self.out_bytes <= out.numel()
         self.contiguous = bool((out_lens == wl["counts"] * np.uint64(wl["vs"])).all())
         items = [(self.blob.data_ptr() + int(wl["offsets"][i]), int(wl["sizes"][i]), out.data_ptr() + int(self.out_offs[i]), int(wl["counts"][i]), wl["vs"], 0) for i in range(n)]
+        torch.cuda.synchronize(dev)  # (plan.create_ms is the plan's own host time: cudaMalloc would wait for the upload above)
         self.plan = mb.Plan(ctx, mb.make_streams(items), sidecars=wl["sidecars"] if block else None)
         self.out = out
 
