@@ -334,8 +334,9 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.walker_lead = ctx->walker_lead;
 	// few streams: one walker WARP per stream (6x lower latency per block); many: one lane per stream
 	// mostly small-vertex blocks and enough streams for the decoders to be the bottleneck (with fewer the walkers set the
-	// pace and a round only waits longer for its members: measured 5-15% slower at 1024 streams): decode in rounds
-	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && n >= (size_t)8 * plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
+	// pace and a round only waits longer for its members: measured 5-15% slower at 1024 streams, even at 2048, 20% faster
+	// at 4096 for 4- and 8-byte vertices): decode in rounds
+	plan->T.rounds = ctx->rounds_mode == 2 ? (small_blocks * 2 > total_blocks && n >= (size_t)4 * plan->grid ? 1u : 0u) : (uint32_t)ctx->rounds_mode;
 	plan->T.wide_walk = ctx->wide_walk_mode == 2 ? (n < (size_t)2 * resident ? 1u : 0u) : (uint32_t)ctx->wide_walk_mode;
 	plan->small_blocks_majority = small_blocks * 2 > total_blocks;
 	plan->wide_walk_choice = (int)plan->T.wide_walk;
