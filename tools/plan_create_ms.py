@@ -1,5 +1,6 @@
-import sys, time
-sys.path.insert(0, '/root/repo')
+"""Host time of mob200_plan_create against the number of streams (three plans per shape, freed in between)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import meshoptimizer_b200 as mb
 ctx = mb.default_context()
