@@ -272,3 +272,42 @@ def test_block_mode_rounds_level_major_still_available(mb, monkeypatch):
         assert (status == 0).all() and guard and _same(w, outs, _expected(w)) is None
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("rounds", ["0", "1", "2"])
+def test_block_mode_differential_shapes(mb, monkeypatch, rounds):
+    """every vertex size class x ragged counts x codec versions / levels in ONE block-mode plan with sidecars, with either
+    decoder form forced and with the plan's own choice: partial blocks of large vertices join rounds (two quanta, more than
+    four 4-byte lanes: never chained), streams of one block, empty streams"""
+    if not loader.have_ref():
+        pytest.skip("needs the reference encoder")
+    R, P = loader.ref(), loader.port()
+    rng = np.random.default_rng(23)
+    blobs, offs, sizes, counts, vss, want, sidecars = [], [], [], [], [], [], []
+    cursor, k = 0, 0
+    for vs in (4, 8, 12, 16, 20, 24, 32, 48, 64, 128, 256):
+        for count in (0, 1, 16, 17, 255, 256, 257, 1030, 4103):
+            version, level = ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3))[k % 5]
+            words = np.cumsum(rng.integers(-3, 4, (count, vs // 4)) << rng.integers(0, 20, (1, vs // 4)), axis=0).astype(np.uint32)
+            v = words.view(np.uint8).reshape(-1)
+            enc = R.encode_vertex_buffer(v.reshape(count, vs) if count else v, count, vs, level, version)
+            rc, sc = P.block_offsets(count, vs, enc)
+            assert rc == 0
+            pad = (-enc.size) % 16
+            blobs.append(np.concatenate([enc, np.zeros(pad, np.uint8)]))
+            offs.append(cursor); sizes.append(enc.size); counts.append(count); vss.append(vs); want.append(v); sidecars.append(sc.copy())
+            cursor += enc.size + pad
+            k += 1
+    n = len(offs)
+    w = workloads.Workload("shapes", np.concatenate(blobs + [np.zeros(32, np.uint8)]), np.array(offs, np.uint64), np.array(sizes, np.uint64),
+                           np.array(counts, np.uint64), np.array(vss, np.uint32), np.zeros(n, np.int32), source=None)
+    monkeypatch.setenv("MOB200_ROUNDS", rounds)
+    ctx = mb.Context(-1)
+    try:
+        outs, status, plan, guard = device_run(w, ctx=ctx, runs=0, sidecars=sidecars, block_runs=2)
+        assert guard and (status == 0).all(), np.nonzero(status)[0][:8]
+        for i in range(n):
+            assert np.array_equal(outs[i], want[i]), (i, counts[i], vss[i], first_mismatch(outs[i], want[i]))
+        del plan
+    finally:
+        ctx.close()
