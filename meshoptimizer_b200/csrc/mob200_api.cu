@@ -43,6 +43,7 @@ struct mob200_Plan
 	const uint2* tickets_level = nullptr; // decode order of the fused walk: level-major inside a wave of streams
 	const uint2* tickets_runs = nullptr;  // block mode + rounds: runs of 1 << run_shift consecutive blocks of a stream (small-vertex plans only)
 	uint32_t run_shift = 0;
+	bool plain_runs = false; // the run-major table is for the plain form (runs of 16), not for rounds
 	bool two_phase = false; // the last run was a team walk + block-mode decode (two launches)
 	// ring of CUDA-event pairs (before / after the fused walk + decode kernel), one per run, recorded on the
 	// launching stream: per-launch durations can be read back after a timed region without any
@@ -263,9 +264,15 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	// share a decode round are four CONSECUTIVE blocks of one stream: inside a round the carries chain through the unit's
 	// own look-back entries, and the first member's predecessor lies four times as many tickets back
 	const bool small_majority = small_blocks * 2 > total_blocks;
-	const uint32_t run_shift = tiny_blocks * 2 > small_blocks ? kRunShiftMax : 1u, kRunBlocks = 1u << run_shift;
-	std::vector<uint2> ticket_runs(small_majority ? total_blocks : 0);
-	if (small_majority)
+	// Plain form (larger vertices), at least as many streams as units: runs of 16 consecutive blocks of a stream per unit.
+	// Inside a run the decoder warps hand the running value from block to block in shared memory (BlockParams::chain); only
+	// a run's first block looks back, at a block 16 x streams tickets earlier, i.e. finished.  (With fewer streams than
+	// units a run would start where another unit's run of the same age ENDS: the units would wait for each other in turn.)
+	const bool plain_runs = !small_majority && n_with_blocks >= plan->grid && ctx->run_major;
+	const uint32_t run_shift = plain_runs ? kPlainRunShift : (tiny_blocks * 2 > small_blocks ? kRunShiftMax : 1u), kRunBlocks = 1u << run_shift;
+	const bool have_runs = small_majority || plain_runs;
+	std::vector<uint2> ticket_runs(have_runs ? total_blocks : 0);
+	if (have_runs)
 	{
 		size_t t = 0;
 		const uint32_t levels = n ? host[0].nblocks : 0; // sorted: the first stream is the longest
@@ -320,7 +327,8 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	plan->T.lookback = reinterpret_cast<unsigned long long*>(base + off_look);
 	plan->T.ticket_info = reinterpret_cast<uint2*>(base + off_tinfo);
 	plan->tickets_level = plan->T.ticket_info;
-	plan->tickets_runs = small_majority ? reinterpret_cast<uint2*>(base + off_truns) : nullptr;
+	plan->tickets_runs = have_runs ? reinterpret_cast<uint2*>(base + off_truns) : nullptr;
+	plan->plain_runs = plain_runs;
 	plan->T.ticket_shift = 0;
 	plan->run_shift = run_shift;
 	plan->T.status = reinterpret_cast<int32_t*>(base + off_status);
@@ -363,7 +371,7 @@ static int plan_create_body(mob200_Context* ctx, const mob200_Stream* streams, s
 	if (total_blocks)
 	{
 		ok = ok && cudaMemcpyAsync(base + off_tinfo, ticket_info.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
-		if (small_majority)
+		if (have_runs)
 			ok = ok && cudaMemcpyAsync(base + off_truns, ticket_runs.data(), total_blocks * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
 	}
 	std::vector<uint32_t> side;
@@ -560,7 +568,7 @@ extern "C" int mob200_plan_run_ex(mob200_Plan* plan, void* cuda_stream, int flag
 			T.rounds = plan->small_blocks_majority ? 1u : 0u;
 	}
 	plan->two_phase = two_phase;
-	const bool run_major = T.block_mode && T.rounds && plan->tickets_runs && plan->ctx->run_major;
+	const bool run_major = T.block_mode && plan->tickets_runs && plan->ctx->run_major && (plan->plain_runs ? !T.rounds : T.rounds != 0);
 	T.ticket_info = run_major ? plan->tickets_runs : plan->tickets_level;
 	T.ticket_shift = run_major ? plan->run_shift : 0u;
 	if (two_phase)

@@ -18,6 +18,7 @@ constexpr uint32_t kGroupReadLimit = 24;   // bytes that must remain readable be
 constexpr uint32_t kTailMinV0 = 32;
 constexpr uint32_t kTailMinV1 = 24;
 
+constexpr uint32_t kPlainRunShift = 4; // plain form, block mode: runs of 16 consecutive blocks of a stream per unit (= half a producer batch)
 constexpr uint32_t kRunShiftMax = 2; // run-major decode order: 1 << shift consecutive blocks of a stream per ticket chunk (= the blocks of a decode round:
                                      // four of <= 8-byte vertices, two of 12- / 16-byte vertices)
 constexpr uint32_t kInvalidOffset = 0xffffffffu; // walk result for a block that must not be decoded

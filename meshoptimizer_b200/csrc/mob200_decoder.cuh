@@ -36,6 +36,8 @@ constexpr uint32_t kStageRingBytes = 14336;    // staging ring: encoded bytes + 
 constexpr uint32_t kPlainRingBytes = MOB200_PLAIN_RING; // plain form: 16 KB measured the same, 18 KB 2 % slower
 constexpr uint32_t kRowsInRingMaxVs = 32;      // rows (32 bytes per byte-channel) travel through the ring up to this vertex size
 constexpr uint32_t kRowsInGlobal = 0xffffffffu;
+constexpr uint32_t kStageSlack = 16;           // bytes of the ring behind a block's encoded window that belong to the block: the unpack's 32-bit windows may
+                                               // reach a few bytes past the last escape byte (never selected) and must not touch the next block's copy
 constexpr uint32_t kTilePad = 8;               // bytes of padding per 16-vertex chunk of the output tile
 
 struct BlockParams // written by the producer, read by the decoders after the slot's `full` barrier (80 bytes)
@@ -84,7 +86,8 @@ struct Lay
 	static constexpr uint32_t kSmemSlots = kSmemPatch + 64;
 	static constexpr uint32_t kSmemBars = kSmemSlots + kSlots * sizeof(SlotData); // full[kSlots], carry[kSlots], empty[kSlots], tile_free
 	static constexpr uint32_t kSmemProducer = kSmemBars + (3 * kSlots + 1) * 8;   // producer-private: ring_start[kSlots], ring_len[kSlots]
-	static constexpr uint32_t kSmemWalker = (kSmemProducer + 2 * kSlots * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
+	static constexpr uint32_t kSmemPrefix = kSmemProducer + 2 * kSlots * 4;       // plain form: the unit's running value per 4-byte lane, two copies (block parity)
+	static constexpr uint32_t kSmemWalker = (kSmemPrefix + 2 * 64 * 4 + 511) & ~511u; // walker warp (either form): rings, tables, barriers
 	static constexpr uint32_t kSmemTotal = (kSmemWalker + 32 * 512 + 6 * 4 * 32 + 16 + 1023) & ~1023u; // one unit
 	static constexpr uint32_t kSmemCta = kSmemTotal * kUnitsPerCta;
 	static_assert(kSmemCta <= 227 * 1024, "shared memory of one CTA");
@@ -93,7 +96,7 @@ struct Lay
 constexpr uint32_t kSmemWalkerBytes = 32 * 512 + 6 * 4 * 32 + 16; // = kWalkSmemBytes (mob200_walker.cuh) >= kWideSmemBytes
 
 static_assert(sizeof(BlockParams) == 80 && sizeof(SlotData) == 416, "SlotData layout");
-static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + 32 * kRowsInRingMaxVs && kPlainRingBytes >= kStageRingBytes && kPlainRingBytes % 16 == 0, "staging ring must hold the largest block");
+static_assert(kStageRingBytes >= kMaxEncodedBlock + 32 + kStageSlack + 32 * kRowsInRingMaxVs && kPlainRingBytes >= kStageRingBytes && kPlainRingBytes % 16 == 0, "staging ring must hold the largest block");
 
 uint32_t decode_smem_bytes()
 {
@@ -247,6 +250,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 	uint32_t head = 0;  // next free byte of the staging ring
 	uint32_t freed = 0; // blocks [freed, i) of this CTA's sequence are in flight (their ring pieces are live)
 	const uint32_t my_count = unit_block_count(T, unit);
+	uint32_t prev_s = 0xffffffffu, prev_b = 0, prev_valid = 0; // the unit's previous block (unit-local chains)
 
 	long long dbg_meta = 0, dbg_slot = 0, dbg_look = 0;
 	const long long dbg_t0 = dbg_clock();
@@ -264,7 +268,8 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 		const uint32_t mi = i0 + lane;
 		const bool has = lane < kBatch && mi < my_count;
 		uint32_t m_valid = 0, m_vs = 4, m_n = 0, m_filter = 0, m_version = 0, m_b = 0, m_enc = 0, m_shift = 0, m_ready = 0;
-		uint32_t m_s = 0xffffffffu; // stream of the block (chained rounds)
+		uint32_t m_s = 0xffffffffu; // stream of the block (chained rounds; unit-local chains of the plain form)
+		uint32_t m_chain = 0;       // plain form, block mode: the unit's previous block is this block's predecessor and decodable
 		uint32_t m_magic = 0;       // ceil(2^32 / (16 * vertex size)): a division, done here for all blocks of the batch at once
 		uint32_t m_quanta = 0, m_len = 0; // rounds variant: decoder work quanta (32 items each) and staged bytes of the block
 		unsigned long long m_lo = 0, m_tail = 0, m_out = 0, m_rows = 0, m_look = 0;
@@ -354,7 +359,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 				m_lo = lo;
 				m_enc = (uint32_t)(hi - lo);
 				m_shift = (uint32_t)(a0 - lo);
-				m_len = m_enc + (vs <= kRowsInRingMaxVs ? 32u * vs : 0u);
+				m_len = m_enc + kStageSlack + (vs <= kRowsInRingMaxVs ? 32u * vs : 0u);
 				if (kRounds)
 				{
 					const uint32_t groups_j = (m_n + kGroup - 1) / kGroup;
@@ -364,6 +369,15 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			}
 		}
 		__syncwarp();
+		if (!kRounds && kBlock)
+		{
+			// (lane - 1 holds the unit's previous block; for lane 0 it is the last block of the previous batch)
+			const uint32_t ps = __shfl_up_sync(0xffffffffu, m_s, 1), pb = __shfl_up_sync(0xffffffffu, m_b, 1), pv = __shfl_up_sync(0xffffffffu, m_valid, 1);
+			const uint32_t qs = lane ? ps : prev_s, qb = lane ? pb : prev_b, qv = lane ? pv : prev_valid;
+			m_chain = (has && m_valid && qv && qs == m_s && qb + 1 == m_b && T.ticket_shift) ? 1u : 0u;
+			const uint32_t lastl = min(kBatch, my_count - i0) - 1;
+			prev_s = __shfl_sync(0xffffffffu, m_s, lastl), prev_b = __shfl_sync(0xffffffffu, m_b, lastl), prev_valid = __shfl_sync(0xffffffffu, m_valid, lastl);
+		}
 		dbg_meta += dbg_clock() - c0;
 		MOB200_TRACE_EVENT(T, unit, lane, 2, i0);
 
@@ -575,6 +589,8 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						P.round_members = lane == j ? cnt : 0u;
 						P.chain = (lane == j && chained) ? 1u : 0u;
 					}
+					else
+						P.chain = m_chain;
 					if (m_valid)
 					{
 						const uint32_t rows_bytes = vs_l <= kRowsInRingMaxVs ? 32u * vs_l : 0u;
@@ -599,7 +615,7 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						P.gshift = gshift;
 						P.items = nq_l << gshift;
 						P.stage_off = at + m_shift;
-						P.rows_off = rows_bytes ? at + m_enc : kRowsInGlobal;
+						P.rows_off = rows_bytes ? at + m_enc + kStageSlack : kRowsInGlobal;
 						P.first = m_b == 0;
 						P.filter = m_filter;
 						P.filter_kind = m_filter == MOB200_FILTER_NONE ? 0u : ((m_filter == MOB200_FILTER_EXP || vs_l == 4) ? 1u : 2u);
@@ -609,10 +625,10 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 						P.lookback = reinterpret_cast<unsigned long long*>(m_look);
 
 						fence_proxy_async(); // the decoders' generic-proxy reads of the reused ring bytes are ordered before the copies
-						mbar_expect_tx(full + slot_l, m_len);
+						mbar_expect_tx(full + slot_l, m_enc + rows_bytes);
 						tma_load_bulk(ring + at, reinterpret_cast<const void*>(m_lo), m_enc, full + slot_l);
 						if (rows_bytes)
-							tma_load_bulk(ring + at + m_enc, P.rows_global, rows_bytes, full + slot_l);
+							tma_load_bulk(ring + at + m_enc + kStageSlack, P.rows_global, rows_bytes, full + slot_l);
 					}
 					else
 					{
@@ -640,8 +656,8 @@ __device__ void producer_main(const DevTables& T, uint8_t* smem, const uint32_t 
 			{
 				const long long c2 = dbg_clock();
 				MOB200_TRACE_EVENT(T, unit, lane, 5, i);
-				bool carry_done = false;
-				if (valid && b > 0 && nq <= 8 && j < kPrefetchBlocks)
+				bool carry_done = !kRounds && kBlock && __shfl_sync(0xffffffffu, m_chain, j) != 0; // the decoders hand the value on
+				if (!carry_done && valid && b > 0 && nq <= 8 && j < kPrefetchBlocks)
 				{
 					// the prefetched look-back entries: good if every one of them is an inclusive prefix of this run
 					const bool mine = (lane >> 1) == j;
@@ -957,6 +973,7 @@ struct BlockRegs
 {
 	uint32_t vs, n, groups, gshift, items, stage_off, rows_off, filter, filter_kind, m_chunk;
 	bool first_block;
+	uint32_t chain; // plain form: the block follows the unit's previous block in its stream: its carry is the unit's running value
 	const uint16_t* rows_global;
 	uint8_t* out;
 	unsigned long long* lookback;
@@ -974,6 +991,7 @@ __device__ __forceinline__ BlockRegs load_block(const SlotData& S)
 	B.rows_global = S.P.rows_global;
 	B.out = S.P.out;
 	B.lookback = S.P.lookback;
+	B.chain = S.P.chain;
 	return B;
 }
 
@@ -991,6 +1009,7 @@ struct DecoderCtx
 	uint64_t* tile_free;
 	unsigned long long tag;
 	uint32_t lane;
+	uint32_t* unit_prefix; // plain form, block mode: the running value the unit hands from a block to the next one of the same stream
 	const DevTables* T; // (event trace)
 	uint32_t unit, warp, index;
 };
@@ -1000,7 +1019,10 @@ struct DecoderCtx
 // kChain (rounds form): the quantum belongs to member `chain_g` of a chained round whose first member sits in slot S0
 // (carry_slot / phase are that member's): the members' aggregates meet in shared memory, one barrier of the decoder
 // warps later every member knows the value in front of it without a look-back through global memory.
-template <bool kChain>
+// kUnit (plain form): a block whose predecessor in the stream was this unit's previous block takes its carry from the
+// unit's running value in shared memory (two copies, by block parity: a block reads one and writes the other) -- no
+// look-back, no global round trip; the producer only completes the carry barrier's phase.
+template <bool kChain, bool kUnit = false>
 __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotData& S, const BlockRegs& B, uint8_t* tile, uint64_t* carry_slot, uint32_t phase,
     uint32_t base, bool first_of_block, uint32_t tile_uses, long long& dbg_carry, long long& dbg_tile, SlotData* slots = nullptr, uint32_t slot0 = 0, uint32_t slot_mask = 0,
     uint32_t chain_g = 0, uint32_t bar_id = 0)
@@ -1190,8 +1212,15 @@ __device__ __forceinline__ void decode_quantum(const DecoderCtx& X, const SlotDa
 		if (kChain)
 			for (uint32_t h = 0; h < chain_g; ++h)
 				carry = lane_combine(carry, slots[(slot0 + h) & slot_mask].chain_total[q], H);
+		if (kUnit && B.chain)
+			carry = X.unit_prefix[(tile_uses & 1u) * 64u + q];
 		if (last)
-			st_volatile_u64(lookback + q, tag | (2ull << 32) | lane_combine(carry, incl, H)); // state 2: inclusive prefix
+		{
+			const uint32_t prefix = lane_combine(carry, incl, H);
+			st_volatile_u64(lookback + q, tag | (2ull << 32) | prefix); // state 2: inclusive prefix
+			if (kUnit)
+				X.unit_prefix[((tile_uses & 1u) ^ 1u) * 64u + q] = prefix;
+		}
 		uint32_t v = lane_combine(carry, excl, H);
 		uint8_t* col = tile + tile_offset(c * 16, vs) + q * 4;
 		// one instruction stream for the three channel modes: a warp whose two lanes differ in mode does not run it twice
@@ -1327,7 +1356,7 @@ __device__ __forceinline__ void release_slot(uint64_t* empty_bar, uint32_t lane)
 	}
 }
 
-template <bool kRounds>
+template <bool kRounds, bool kBlock>
 __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t unit, const uint32_t tid, const uint32_t bar_id)
 {
 	using L = Lay<kRounds>;
@@ -1347,6 +1376,7 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 	X.tile_free = tile_free;
 	X.tag = (unsigned long long)(T.epoch << 2) << 32;
 	X.lane = lane;
+	X.unit_prefix = reinterpret_cast<uint32_t*>(smem + L::kSmemPrefix);
 	X.T = &T, X.unit = unit, X.warp = tid >> 5, X.index = 0;
 	uint32_t tile_uses = 0;
 	long long dbg_full = 0, dbg_carry = 0, dbg_tile = 0;
@@ -1377,14 +1407,16 @@ __device__ void decoder_main(const DevTables& T, uint8_t* smem, const uint32_t u
 			MOB200_TRACE_EVENT(T, unit, lane, 32 + X.warp * 8 + 1, i);
 			// ---- one block: its quanta go round the four warps ---------------------------------------------------------
 			++i;
-			if (!S.P.valid)
+			// (lane 0 reads the flag for the warp: it is the lane that hands the slot back below, and compute-sanitizer's
+			// racecheck credits an arrival only to the arriving thread)
+			if (!__shfl_sync(0xffffffffu, lane == 0 ? S.P.valid : 0u, 0))
 			{
 				release_slot<kRounds>(empty + slot, lane);
 				continue;
 			}
 			const BlockRegs B = load_block(S);
 			for (uint32_t base = warp_base; base < B.items; base += kDecodeThreads)
-				decode_quantum<false>(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
+				decode_quantum<false, !kRounds && kBlock>(X, S, B, tile, carry_bar + slot, phase, base, base == warp_base, tile_uses, dbg_carry, dbg_tile);
 			++tile_uses;
 
 			// this warp no longer needs the slot (staging bytes, rows, params, carry)

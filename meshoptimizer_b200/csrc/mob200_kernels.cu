@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kCtaThreads, 1) decode_kernel(DevTables T)
 	if (role == 0)
 	{
 		if (decode_on)
-			decoder_main<kRounds>(T, smem, unit, utid, 1u + g);
+			decoder_main<kRounds, kBlock>(T, smem, unit, utid, 1u + g);
 	}
 	else if (role == 1)
 	{

@@ -311,3 +311,46 @@ def test_block_mode_differential_shapes(mb, monkeypatch, rounds):
         del plan
     finally:
         ctx.close()
+
+
+def test_block_mode_unit_chains_many_streams(mb):
+    """plain form, at least as many streams as decode units: run-major order with runs of 16 blocks per unit, the decoder
+    warps hand the running value from block to block (no look-back inside a run).  1500 streams x 11 blocks (ragged last
+    block), one stream with a stale sidecar entry in the middle of its run, one with bad magic: the others bit-exact."""
+    w = workloads.c2(total=1500 * 2700, seg=2700, level=2, version=1)
+    assert w.n == 1500
+    want = _expected(w)
+    sc = _sidecars(w)
+    bad = [s.copy() for s in sc]
+    bad[700][5] += 2                      # block 5 of stream 700 starts two bytes late
+    blob = w.blob.copy()
+    blob[int(w.offsets[33])] = 0x10       # bad magic
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=bad, block_runs=2, blob_override=blob)
+    assert guard
+    assert status[700] == mb.ERR_SIDECAR and status[33] == -1
+    ok = [i for i in range(w.n) if i not in (33, 700)]
+    assert (status[ok] == 0).all()
+    for i in ok:
+        assert np.array_equal(outs[i], want[i]), (i, first_mismatch(outs[i], want[i]))
+    # the serial walk of the same plan (level-major, no chains) gives the reference result for the stale one as well
+    outs, status, plan, guard = device_run(w, runs=1)
+    assert (status == 0).all() and _same(w, outs, want) is None
+
+
+def test_block_mode_unit_chains_long_streams(mb):
+    """800 streams x 40 blocks: a stream is three runs (16 + 16 + 8 blocks) on three different units, so every run start
+    looks back across units while the blocks inside a run chain; 64-byte vertices (two quanta per warp and block)"""
+    rng = np.random.default_rng(4)
+    total, vs, seg = 800 * 40 * 128, 64, 40 * 128
+    words = np.cumsum(rng.integers(-50, 50, (total, vs // 4)), axis=0).astype(np.uint32)
+    v = words.view(np.uint8).reshape(-1)
+    blob, segs, side = mb.encode_segments(v, total, vs, seg, 2, 1, threads=0)
+    n = len(segs)
+    assert n == 800
+    w = workloads.Workload("chains64", np.concatenate([blob, np.zeros(32, np.uint8)]),
+                           np.array([s.offset for s in segs], np.uint64), np.array([s.size for s in segs], np.uint64),
+                           np.array([s.vertex_count for s in segs], np.uint64), np.full(n, vs, np.uint32), np.zeros(n, np.int32), source=v)
+    sidecars = [side[s.sidecar_offset : s.sidecar_offset + s.sidecar_entries] for s in segs]
+    outs, status, plan, guard = device_run(w, runs=0, sidecars=sidecars, block_runs=2)
+    assert guard and (status == 0).all()
+    assert np.array_equal(np.concatenate(outs), v)
